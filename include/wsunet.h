@@ -1,0 +1,105 @@
+/* libwsunet — C ABI of the B200-native UNet -> Weighted-Stego (WS) hot path.
+ *
+ * The reference (uibk-uncover/ws-unet) is pure Python and has no FFI of its own: its
+ * boundary is three duck-typed Python interfaces. Each entry point below names the reference call it serves;
+ * the Python shim in ws_unet_b200/ binds them with ctypes and re-exposes the reference's own signatures.
+ *
+ * Conventions: every function returns 0 on success or a negative wsu_status; wsu_last_error() returns a
+ * thread-local message for the last failure. Pointers named *_dev are device pointers owned by the caller on the
+ * handle's device; the library never frees caller memory. `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream). A handle is bound to one device and must be used by one host thread at a time.
+ * There is no CPU fallback: on a machine without a CUDA device every compute entry point fails with
+ * WSU_ERR_CUDA.
+ */
+#ifndef WSUNET_H_
+#define WSUNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wsu_context* wsu_handle;
+
+enum wsu_status {
+  WSU_OK = 0,
+  WSU_ERR_INVALID = -1, /* bad argument / unsupported configuration (Python shim raises ValueError/NotImplementedError) */
+  WSU_ERR_CUDA = -2,    /* CUDA runtime/driver failure (RuntimeError) */
+  WSU_ERR_STATE = -3    /* weights missing / not committed */
+};
+
+enum wsu_dtype { WSU_U8 = 0, WSU_F32 = 1 };
+
+/* linear predictors: src/ws/estimate.py:31-52 and src/filters/evaluate.py:29-50 (NAMED_FILTERS[_2D]) */
+enum wsu_predictor { WSU_PRED_KB = 0, WSU_PRED_AVG = 1, WSU_PRED_AVG9 = 2, WSU_PRED_ID = 3 };
+
+/* `weighted` argument of attack(): src/ws/estimate.py:55-110 */
+enum wsu_weighting { WSU_UNWEIGHTED = 0, WSU_WEIGHTED = 1, WSU_ANTIWEIGHTED = -1 };
+
+const char* wsu_last_error(void);
+int wsu_version(void);
+
+/* ---- predictor module: src/unet/model/__init__.py:8-27 get_model('unet_<nsteps>', in_channels, out_channels) and
+ *      src/unet/model/unet.py:54-135 UNet.__init__. out_channels must be 1 (the only value the reference uses). */
+int wsu_create(wsu_handle* out, int device, int nsteps, int in_channels, int out_channels);
+int wsu_destroy(wsu_handle h);
+
+/* nn.Module.load_state_dict (src/unet/evaluate.py:184-186): one call per state_dict entry, e.g. "e11.weight" with
+ * dims (64,in,3,3), "upconv3.weight" with dims (256,128,2,2), "outconv.bias" with dims (1). `data` is HOST fp32 in
+ * PyTorch's contiguous layout. wsu_commit_weights() packs (split-bf16, tile-swizzled) and uploads. */
+int wsu_load_weights(wsu_handle h, const char* name, const float* data, const int64_t* dims, int ndims);
+int wsu_commit_weights(wsu_handle h);
+
+/* options: "micro_batch" (images per pass through the layer chain; 0 = auto) */
+int wsu_set_option(wsu_handle h, const char* key, int64_t value);
+
+/* UNet.forward (src/unet/model/unet.py:137-189): x_dev (B,in_channels,H,W) in [0,1] as float32, or uint8 pixels
+ * (then x/255 is applied as in src/unet/evaluate.py:45) -> y_dev (B,1,H,W) float32 sigmoid output in (0,1).
+ * H and W must be divisible by 2^nsteps and >= 2 at the deepest level (same constraint as the reference). */
+int wsu_unet_forward(wsu_handle h, const void* x_dev, int x_dtype, float* y_dev, int B, int H, int W, void* stream);
+
+/* Fused UNet predictor -> WS estimator. Semantics:
+ *   crop=1, weighted=0, clip=0 : src/unet/evaluate.py:109-139 predict_unet   (beta_hat, l1)
+ *   crop=1, weighted in {0,1,-1}, clip=1 : src/ws/estimate.py:55-136 attack with the UNet pixel_estimator
+ *   crop=0, weighted=0, clip=1 : src/_defs/losses.py:46-61 WSLoss._error betas_hat (float images allowed)
+ * img_dev (B,1,H,W) uint8 or float32 in [0,1]; beta_dev (B) float32; l1_dev (B) or NULL; yhat_dev (B,1,H,W) or NULL. */
+int wsu_unet_ws_estimate(wsu_handle h, const void* img_dev, int img_dtype, int B, int H, int W, int weighted, int clip,
+                         int crop, float* beta_dev, float* l1_dev, float* yhat_dev, void* stream);
+
+/* Same, but img_host/beta_host/l1_host are HOST buffers: chunks are copied H2D on a side stream overlapping compute,
+ * results copied back; returns after everything has completed. This is the end-to-end call bench.py times. */
+int wsu_unet_ws_estimate_host(wsu_handle h, const uint8_t* img_host, int B, int H, int W, int weighted, int clip, int crop,
+                              float* beta_host, float* l1_host);
+
+/* ---- linear predictors, no handle needed: src/filters/evaluate.py:136-146 infere_single/get_filter_estimator.
+ * xhat_dev (B,H-2,W-2) float32 in pixel units ('valid' 3x3 correlation). */
+int wsu_filter_predict(int device, const void* img_dev, int img_dtype, int kind, float* xhat_dev, int B, int H, int W,
+                       void* stream);
+
+/* src/ws/estimate.py:55-136 attack with a NAMED_FILTERS pixel_estimator, mean_estimator=AVG; one pass over the image. */
+int wsu_filter_ws_estimate(int device, const void* img_dev, int img_dtype, int kind, int weighted, int clip,
+                           int correct_bias, float* beta_dev, float* l1_dev, int B, int H, int W, void* stream);
+int wsu_filter_ws_estimate_host(int device, const uint8_t* img_host, int kind, int weighted, int clip, int correct_bias,
+                                float* beta_host, float* l1_host, int B, int H, int W);
+
+/* WS reduction against caller-supplied predictions in pixel units (any pixel_estimator; also the second pass of
+ * correct_bias, src/ws/estimate.py:126-128). xhat_cropped=1: xhat/xbias are (B,H-2,W-2); 0: (B,H,W).
+ * xbias_dev may be NULL (no bias correction). */
+int wsu_ws_from_prediction(int device, const void* img_dev, int img_dtype, const float* xhat_dev, int xhat_cropped,
+                           const float* xbias_dev, int weighted, int clip, int crop, float* beta_dev, float* l1_dev, int B,
+                           int H, int W, void* stream);
+
+/* ---- introspection for the per-layer parity tests: copy a feature map of the LAST micro-batch of the last forward
+ * as float32 NCHW (hi+lo recombined). name in {"e11","e12","p1","e21",...,"u3","d31","d32",...}. with_halo=1 returns
+ * (B,C,H+2,W+2) including the materialised reflect border. dims_out receives (B,C,H,W) of the returned tensor. */
+int wsu_debug_layer(wsu_handle h, const char* name, float* dst_dev, size_t dst_capacity_elems, int with_halo,
+                    int64_t* dims_out, void* stream);
+/* number of kernels launched by this library in the calling thread since the last call (bench.py gpu_launches) */
+int64_t wsu_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WSUNET_H_ */

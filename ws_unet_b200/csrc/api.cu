@@ -1,0 +1,725 @@
+// C ABI of libwsunet (include/wsunet.h): handle, weight packing, per-shape plan (buffers + TMA tensor maps),
+// layer chain of UNet.forward (src/unet/model/unet.py:137-189) and the fused / stand-alone WS estimators.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/wsunet.h"
+#include "conv_mma.h"
+#include "stencil.h"
+
+using namespace wsu;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int64_t g_launches = 0;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(WSU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+#define LAUNCH_TRY(expr)                                                                           \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    ++g_launches;                                                                                  \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(WSU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------- bf16 on the host
+uint16_t f2bf(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return uint16_t((u >> 16) | 0x40);  // NaN
+  const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+  return uint16_t((u + r) >> 16);
+}
+float bf2f(uint16_t h) {
+  uint32_t u = uint32_t(h) << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+inline size_t sw128_off(int row, int k) {  // byte offset of bf16 element (row, k) inside a K-major SWIZZLE_128B tile
+  return size_t(row) * 128 + size_t(((k >> 3) ^ (row & 7)) << 4) + size_t(k & 7) * 2;
+}
+
+// ---------------------------------------------------------------------------------------------- driver entry point
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 5-D map over a split-bf16 NHWC activation: dims (C, W+2, H+2, B, plane), box (64, TW, TH, 1, 2)
+int make_act_tmap(CUtensorMap* m, const Act& a, int TW, int TH) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(WSU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t Wp = a.W + 2, Hp = a.H + 2;
+  cuuint64_t dims[5] = {cuuint64_t(a.C), Wp, Hp, cuuint64_t(a.B), 2};
+  cuuint64_t strides[4] = {cuuint64_t(a.C) * 2, Wp * a.C * 2, Hp * Wp * a.C * 2, cuuint64_t(a.plane) * 2};
+  cuuint32_t box[5] = {64, cuuint32_t(TW), cuuint32_t(TH), 1, 2};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, a.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(WSU_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
+  return WSU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- model description
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> dims;
+};
+
+struct LayerW {  // device-side packed weights of one tensor-core layer
+  uint8_t* wpack = nullptr;
+  float* bias = nullptr;
+  int cin = 0, cout = 0, n_tile = 0, ntaps = 0, npos = 0;
+};
+
+struct Plan {  // everything that depends on (micro-batch, H, W)
+  int mb = 0, H = 0, W = 0;
+  std::map<std::string, Act> acts;
+  std::vector<void*> allocs;
+  float* partials = nullptr;
+  int tiles_per_img = 0;
+  std::vector<std::pair<ConvParams, std::pair<int, int>>> convs;  // params, (n_tile, epi); head is the last entry
+};
+
+}  // namespace
+
+struct wsu_context {
+  int device = 0, nsteps = 0, in_ch = 1, out_ch = 1, num_sms = 148;
+  int64_t micro_batch = 0;
+  std::map<std::string, HostTensor> host_w;
+  bool committed = false;
+  std::map<std::string, LayerW> layers;
+  float* e11_w = nullptr;
+  float* e11_b = nullptr;
+  float wout[64];
+  float bout = 0.f;
+  std::unique_ptr<Plan> plan;
+  // host-path staging
+  uint8_t* stage_img[2] = {nullptr, nullptr};
+  float* stage_out = nullptr;
+  size_t stage_imgs = 0, stage_px = 0;
+  cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+std::string enc_name(int level, int idx) { return "e" + std::to_string(level + 1) + std::to_string(idx); }
+std::string dec_name(int level, int idx) { return "d" + std::to_string(4 - level) + std::to_string(idx); }
+std::string up_name(int level) { return "upconv" + std::to_string(4 - level); }
+int chan(int level) { return 64 << level; }
+
+void free_plan(Plan* p) {
+  if (!p) return;
+  for (void* q : p->allocs) cudaFree(q);
+  p->allocs.clear();
+}
+
+int alloc_act(Plan& pl, const std::string& name, int B, int H, int W, int C) {
+  Act a;
+  a.B = B; a.H = H; a.W = W; a.C = C;
+  a.plane = act_plane_elems(B, H, W, C);
+  void* p = nullptr;
+  const size_t bytes = a.plane * 2 * sizeof(__nv_bfloat16);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(WSU_ERR_CUDA, "cudaMalloc(" + name + ", " + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
+  // borders that no producer writes (none today) and overhanging reads stay finite
+  cudaMemset(p, 0, bytes);
+  a.base = static_cast<__nv_bfloat16*>(p);
+  pl.allocs.push_back(p);
+  pl.acts[name] = a;
+  return WSU_OK;
+}
+
+size_t per_image_bytes(int nsteps, int H, int W) {
+  size_t total = 0;
+  auto add = [&](int l, int c) { total += size_t(H >> l) * (W >> l) * c * 4; };
+  for (int l = 0; l <= nsteps; ++l) {
+    add(l, chan(l));
+    add(l, chan(l));
+    if (l < nsteps) add(l + 1, chan(l));
+  }
+  for (int l = nsteps - 1; l >= 0; --l) {
+    add(l, chan(l));
+    add(l, chan(l));
+    add(l, chan(l));
+  }
+  return total + total / 8;
+}
+
+// Build a conv step. src1 may be null (no concat).
+int add_conv(wsu_context* h, Plan& pl, const LayerW& lw, const Act& src0, const Act* src1, const Act* out, const Act* pool,
+             bool upsample, bool relu, int epi) {
+  ConvParams p;
+  std::memset(&p, 0, sizeof(p));
+  const int TW = 16, TH = 8;
+  const int m_sub = 256 / lw.n_tile;
+  int rc = make_act_tmap(&p.tmapA0, src0, TW, TH);
+  if (rc) return rc;
+  rc = make_act_tmap(&p.tmapA1, src1 ? *src1 : src0, TW, TH);
+  if (rc) return rc;
+  p.wpack = lw.wpack;
+  p.bias = lw.bias;
+  p.cblocks0 = src0.C / 64;
+  p.cblocks = lw.cin / 64;
+  p.ntaps = lw.ntaps;
+  for (int t = 0; t < 9; ++t) {
+    p.tap_dx[t] = (lw.ntaps == 9) ? t % 3 : 1;
+    p.tap_dy[t] = (lw.ntaps == 9) ? t / 3 : 1;
+  }
+  p.npos = lw.npos;
+  p.n_tiles = lw.cout / lw.n_tile;
+  p.cout = lw.cout;
+  p.B = src0.B; p.H = src0.H; p.W = src0.W;
+  p.TW = TW; p.TH = TH;
+  p.tiles_x = (p.W + TW * m_sub - 1) / (TW * m_sub);
+  p.tiles_y = (p.H + TH - 1) / TH;
+  p.total_tiles = p.B * p.tiles_y * p.tiles_x * p.n_tiles * p.npos;
+  p.relu = relu;
+  p.upsample = upsample;
+  if (out) p.out = *out;
+  if (pool) { p.do_pool = 1; p.pool = *pool; }
+  if (epi == EPI_HEAD) {
+    std::memcpy(p.wout, h->wout, sizeof(p.wout));
+    p.bout = h->bout;
+    pl.tiles_per_img = p.tiles_x * p.tiles_y;
+  }
+  pl.convs.push_back({p, {lw.n_tile, epi}});
+  return WSU_OK;
+}
+
+int build_plan(wsu_context* h, int mb, int H, int W) {
+  if (h->plan && h->plan->mb >= mb && h->plan->H == H && h->plan->W == W) return WSU_OK;
+  if (h->plan) { cudaDeviceSynchronize(); free_plan(h->plan.get()); }
+  h->plan.reset(new Plan());
+  Plan& pl = *h->plan;
+  pl.mb = mb; pl.H = H; pl.W = W;
+  const int n = h->nsteps;
+  int rc;
+  // activations
+  for (int l = 0; l <= n; ++l) {
+    const int hh = H >> l, ww = W >> l;
+    if ((rc = alloc_act(pl, enc_name(l, 1), mb, hh, ww, chan(l)))) return rc;
+    if (!(n == 0)) {
+      if ((rc = alloc_act(pl, enc_name(l, 2), mb, hh, ww, chan(l)))) return rc;
+    }
+    if (l < n) {
+      if ((rc = alloc_act(pl, "p" + std::to_string(l + 1), mb, hh / 2, ww / 2, chan(l)))) return rc;
+    }
+  }
+  for (int l = n - 1; l >= 0; --l) {
+    const int hh = H >> l, ww = W >> l;
+    if ((rc = alloc_act(pl, "u" + std::to_string(4 - l), mb, hh, ww, chan(l)))) return rc;
+    if ((rc = alloc_act(pl, dec_name(l, 1), mb, hh, ww, chan(l)))) return rc;
+    if (l > 0) {
+      if ((rc = alloc_act(pl, dec_name(l, 2), mb, hh, ww, chan(l)))) return rc;
+    }
+  }
+  // layer chain (first conv is launched separately)
+  auto A = [&](const std::string& s) -> Act& { return pl.acts.at(s); };
+  for (int l = 0; l <= n; ++l) {
+    if (l > 0) {
+      if ((rc = add_conv(h, pl, h->layers.at(enc_name(l, 1)), A("p" + std::to_string(l)), nullptr, &A(enc_name(l, 1)), nullptr,
+                         false, true, EPI_ACT)))
+        return rc;
+    }
+    if (n == 0) {
+      if ((rc = add_conv(h, pl, h->layers.at(enc_name(0, 2)), A(enc_name(0, 1)), nullptr, nullptr, nullptr, false, true, EPI_HEAD)))
+        return rc;
+    } else {
+      const Act* pool = (l < n) ? &A("p" + std::to_string(l + 1)) : nullptr;
+      if ((rc = add_conv(h, pl, h->layers.at(enc_name(l, 2)), A(enc_name(l, 1)), nullptr, &A(enc_name(l, 2)), pool, false, true,
+                         EPI_ACT)))
+        return rc;
+    }
+  }
+  for (int l = n - 1; l >= 0; --l) {
+    const std::string below = (l + 1 == n) ? enc_name(l + 1, 2) : dec_name(l + 1, 2);
+    const std::string u = "u" + std::to_string(4 - l);
+    if ((rc = add_conv(h, pl, h->layers.at(up_name(l)), A(below), nullptr, &A(u), nullptr, true, false, EPI_ACT))) return rc;
+    if ((rc = add_conv(h, pl, h->layers.at(dec_name(l, 1)), A(u), &A(enc_name(l, 2)), &A(dec_name(l, 1)), nullptr, false, true,
+                       EPI_ACT)))
+      return rc;
+    if (l > 0) {
+      if ((rc = add_conv(h, pl, h->layers.at(dec_name(l, 2)), A(dec_name(l, 1)), nullptr, &A(dec_name(l, 2)), nullptr, false, true,
+                         EPI_ACT)))
+        return rc;
+    } else {
+      if ((rc = add_conv(h, pl, h->layers.at(dec_name(l, 2)), A(dec_name(l, 1)), nullptr, nullptr, nullptr, false, true, EPI_HEAD)))
+        return rc;
+    }
+  }
+  void* pp = nullptr;
+  CUDA_TRY(cudaMalloc(&pp, size_t(mb) * pl.tiles_per_img * 4 * kPartialSlots * sizeof(float)));
+  pl.allocs.push_back(pp);
+  pl.partials = static_cast<float*>(pp);
+  return WSU_OK;
+}
+
+int check_shape(wsu_context* h, int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return fail(WSU_ERR_INVALID, "B, H, W must be positive");
+  const int div = 1 << h->nsteps;
+  if (H % div || W % div)
+    return fail(WSU_ERR_INVALID, "H and W must be divisible by 2^nsteps (torch.cat would raise in the reference, unet.py:178)");
+  if ((H >> h->nsteps) < 2 || (W >> h->nsteps) < 2)
+    return fail(WSU_ERR_INVALID, "reflect padding needs >= 2 pixels per dimension at the deepest level");
+  return WSU_OK;
+}
+
+int pick_micro_batch(wsu_context* h, int B, int H, int W) {
+  if (h->micro_batch > 0) return int(std::min<int64_t>(h->micro_batch, B));
+  const size_t budget = size_t(20) << 30;
+  int mb = int(std::max<size_t>(1, budget / per_image_bytes(h->nsteps, H, W)));
+  mb = std::min(mb, 64);
+  return std::min(mb, B);
+}
+
+// one micro-batch through the layer chain. img points at this micro-batch's first image.
+int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const void* ws_img, int ws_dtype, float* yhat,
+              int weighted, int crop, cudaStream_t st) {
+  Plan& pl = *h->plan;
+  Act first = pl.acts.at(enc_name(0, 1));
+  // a short last micro-batch reuses the plan: only the first `nimg` images of each buffer are live
+  LAUNCH_TRY(launch_first_conv(img, img_dtype == WSU_F32, h->in_ch, h->e11_w, h->e11_b,
+                               Act{first.base, first.plane, nimg, first.H, first.W, first.C}, st));
+  for (size_t i = 0; i < pl.convs.size(); ++i) {
+    ConvParams p = pl.convs[i].first;
+    const int n_tile = pl.convs[i].second.first, epi = pl.convs[i].second.second;
+    if (nimg != pl.mb) {
+      p.B = nimg;
+      p.total_tiles = nimg * p.tiles_y * p.tiles_x * p.n_tiles * p.npos;
+    }
+    if (epi == EPI_HEAD) {
+      p.img = ws_img;
+      p.img_is_float = (ws_dtype == WSU_F32);
+      p.yhat = yhat;
+      p.partials = ws_img ? pl.partials : nullptr;
+      p.weighted = weighted;
+      p.crop = crop;
+    }
+    LAUNCH_TRY(launch_conv_mma(p, n_tile, epi, h->num_sms, st));
+  }
+  return WSU_OK;
+}
+
+int unet_ws_device(wsu_context* h, const void* img, int dtype, int B, int H, int W, bool want_ws, int weighted, int clip,
+                   int crop, float* beta, float* l1, float* yhat, cudaStream_t st) {
+  if (!h) return fail(WSU_ERR_INVALID, "null handle");
+  if (!h->committed) return fail(WSU_ERR_STATE, "weights not committed (call wsu_commit_weights)");
+  int rc = check_shape(h, B, H, W);
+  if (rc) return rc;
+  if (dtype != WSU_U8 && dtype != WSU_F32) return fail(WSU_ERR_INVALID, "dtype must be WSU_U8 or WSU_F32");
+  if (want_ws) {
+    if (h->in_ch != 1) return fail(WSU_ERR_INVALID, "the WS estimator is defined for single-channel images");
+    if (weighted < -1 || weighted > 1) return fail(WSU_ERR_INVALID, "weighted must be -1, 0 or 1");
+    if (weighted != 0 && !crop)
+      return fail(WSU_ERR_INVALID, "local-variance weights exist only on the interior (crop=1), estimate.py:94-96");
+    if (crop && (H < 3 || W < 3)) return fail(WSU_ERR_INVALID, "crop=1 needs H, W >= 3");
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int mb = pick_micro_batch(h, B, H, W);
+  if ((rc = build_plan(h, mb, H, W))) return rc;
+  const size_t px = size_t(H) * W;
+  const size_t esz = dtype == WSU_F32 ? 4 : 1;
+  for (int b0 = 0; b0 < B; b0 += mb) {
+    const int nimg = std::min(mb, B - b0);
+    const uint8_t* im = static_cast<const uint8_t*>(img) + size_t(b0) * h->in_ch * px * esz;
+    if ((rc = run_chain(h, im, dtype, nimg, want_ws ? im : nullptr, dtype, yhat ? yhat + size_t(b0) * px : nullptr, weighted, crop,
+                        st)))
+      return rc;
+    if (want_ws) {
+      const float npix = crop ? float(H - 2) * float(W - 2) : float(H) * float(W);
+      LAUNCH_TRY(launch_finalize(h->plan->partials, h->plan->tiles_per_img * 4, nimg, npix, clip, 0, beta + b0,
+                                 l1 ? l1 + b0 : nullptr, st));
+    }
+  }
+  return WSU_OK;
+}
+
+int filter_common_check(const void* img, int dtype, int kind, int B, int H, int W) {
+  if (!img) return fail(WSU_ERR_INVALID, "null image pointer");
+  if (dtype != WSU_U8 && dtype != WSU_F32) return fail(WSU_ERR_INVALID, "dtype must be WSU_U8 or WSU_F32");
+  if (kind < WSU_PRED_KB || kind > WSU_PRED_ID) return fail(WSU_ERR_INVALID, "unknown predictor kind");
+  if (B <= 0 || H < 3 || W < 3) return fail(WSU_ERR_INVALID, "need B >= 1 and H, W >= 3 ('valid' 3x3)");
+  return WSU_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ exported
+extern "C" {
+
+const char* wsu_last_error(void) { return g_err.c_str(); }
+int wsu_version(void) { return 100; }
+int64_t wsu_launch_count(int reset) {
+  const int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int wsu_create(wsu_handle* out, int device, int nsteps, int in_channels, int out_channels) {
+  if (!out) return fail(WSU_ERR_INVALID, "null out pointer");
+  if (nsteps < 0 || nsteps > 4) return fail(WSU_ERR_INVALID, "nsteps must be in 0..4 (unet.py:66,99-132)");
+  if (in_channels < 1 || in_channels > 16) return fail(WSU_ERR_INVALID, "in_channels must be in 1..16");
+  if (out_channels != 1) return fail(WSU_ERR_INVALID, "only out_channels=1 is implemented (the reference never uses another value)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(WSU_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libwsunet has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(WSU_ERR_INVALID, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(WSU_ERR_CUDA, "libwsunet is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+  CUDA_TRY(conv_mma_init());
+  wsu_context* h = new wsu_context();
+  h->device = device;
+  h->nsteps = nsteps;
+  h->in_ch = in_channels;
+  h->out_ch = out_channels;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return WSU_OK;
+}
+
+int wsu_destroy(wsu_handle h) {
+  if (!h) return WSU_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  free_plan(h->plan.get());
+  for (auto& kv : h->layers) { cudaFree(kv.second.wpack); cudaFree(kv.second.bias); }
+  cudaFree(h->e11_w);
+  cudaFree(h->e11_b);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->stage_img[i]);
+    if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+    if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
+  }
+  cudaFree(h->stage_out);
+  if (h->s_copy) cudaStreamDestroy(h->s_copy);
+  if (h->s_comp) cudaStreamDestroy(h->s_comp);
+  delete h;
+  return WSU_OK;
+}
+
+int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
+  if (!h || !key) return fail(WSU_ERR_INVALID, "null argument");
+  if (!std::strcmp(key, "micro_batch")) {
+    if (value < 0) return fail(WSU_ERR_INVALID, "micro_batch must be >= 0");
+    h->micro_batch = value;
+    return WSU_OK;
+  }
+  return fail(WSU_ERR_INVALID, std::string("unknown option ") + key);
+}
+
+int wsu_load_weights(wsu_handle h, const char* name, const float* data, const int64_t* dims, int ndims) {
+  if (!h || !name || !data || !dims || ndims < 1 || ndims > 4) return fail(WSU_ERR_INVALID, "bad argument");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndims; ++i) {
+    if (dims[i] <= 0) return fail(WSU_ERR_INVALID, "non-positive dim");
+    t.dims.push_back(dims[i]);
+    n *= size_t(dims[i]);
+  }
+  t.data.assign(data, data + n);
+  h->host_w[name] = std::move(t);
+  h->committed = false;
+  return WSU_OK;
+}
+
+static int expect_dims(wsu_context* h, const std::string& name, std::vector<int64_t> want, const HostTensor** out) {
+  auto it = h->host_w.find(name);
+  if (it == h->host_w.end()) return fail(WSU_ERR_STATE, "missing state_dict entry '" + name + "'");
+  if (it->second.dims != want) {
+    std::string s = "size mismatch for " + name + ": got (";
+    for (auto d : it->second.dims) s += std::to_string(d) + ",";
+    s += ") expected (";
+    for (auto d : want) s += std::to_string(d) + ",";
+    return fail(WSU_ERR_INVALID, s + ")");
+  }
+  *out = &it->second;
+  return WSU_OK;
+}
+
+static int upload_layer(wsu_context* h, const std::string& name, int cin, int cout, bool transposed) {
+  const HostTensor *w, *b;
+  int rc;
+  if (transposed) {
+    if ((rc = expect_dims(h, name + ".weight", {cin, cout, 2, 2}, &w))) return rc;
+  } else {
+    if ((rc = expect_dims(h, name + ".weight", {cout, cin, 3, 3}, &w))) return rc;
+  }
+  if ((rc = expect_dims(h, name + ".bias", {cout}, &b))) return rc;
+  LayerW lw;
+  lw.cin = cin; lw.cout = cout;
+  lw.n_tile = cout == 64 ? 64 : 128;
+  lw.ntaps = transposed ? 1 : 9;
+  lw.npos = transposed ? 4 : 1;
+  const int n_tiles = cout / lw.n_tile, cblocks = cin / 64, KB = cblocks * lw.ntaps;
+  const size_t chunk = size_t(wchunk_bytes(lw.n_tile));
+  std::vector<uint8_t> pack(size_t(lw.npos) * n_tiles * KB * chunk, 0);
+  for (int pos = 0; pos < lw.npos; ++pos)
+    for (int nt = 0; nt < n_tiles; ++nt)
+      for (int c = 0; c < cblocks; ++c)
+        for (int tap = 0; tap < lw.ntaps; ++tap) {
+          uint8_t* hi = pack.data() + (size_t(pos * n_tiles + nt) * KB + size_t(c) * lw.ntaps + tap) * chunk;
+          uint8_t* lo = hi + size_t(lw.n_tile) * 128;
+          for (int n = 0; n < lw.n_tile; ++n)
+            for (int k = 0; k < 64; ++k) {
+              const int co = nt * lw.n_tile + n, ci = c * 64 + k;
+              float v;
+              if (transposed)
+                v = w->data[((size_t(ci) * cout + co) * 2 + (pos >> 1)) * 2 + (pos & 1)];
+              else
+                v = w->data[((size_t(co) * cin + ci) * 3 + tap / 3) * 3 + tap % 3];
+              const uint16_t vh = f2bf(v);
+              const uint16_t vl = f2bf(v - bf2f(vh));
+              std::memcpy(hi + sw128_off(n, k), &vh, 2);
+              std::memcpy(lo + sw128_off(n, k), &vl, 2);
+            }
+        }
+  auto old = h->layers.find(name);
+  if (old != h->layers.end()) { cudaFree(old->second.wpack); cudaFree(old->second.bias); }
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&lw.wpack), pack.size()));
+  CUDA_TRY(cudaMemcpy(lw.wpack, pack.data(), pack.size(), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&lw.bias), size_t(cout) * 4));
+  CUDA_TRY(cudaMemcpy(lw.bias, b->data.data(), size_t(cout) * 4, cudaMemcpyHostToDevice));
+  h->layers[name] = lw;
+  return WSU_OK;
+}
+
+int wsu_commit_weights(wsu_handle h) {
+  if (!h) return fail(WSU_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaDeviceSynchronize());
+  int rc;
+  const int n = h->nsteps;
+  // e11: CUDA-core first layer keeps fp32 weights
+  const HostTensor *w, *b;
+  if ((rc = expect_dims(h, "e11.weight", {64, h->in_ch, 3, 3}, &w))) return rc;
+  if ((rc = expect_dims(h, "e11.bias", {64}, &b))) return rc;
+  cudaFree(h->e11_w);
+  cudaFree(h->e11_b);
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->e11_w), w->data.size() * 4));
+  CUDA_TRY(cudaMemcpy(h->e11_w, w->data.data(), w->data.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->e11_b), 64 * 4));
+  CUDA_TRY(cudaMemcpy(h->e11_b, b->data.data(), 64 * 4, cudaMemcpyHostToDevice));
+  for (int l = 0; l <= n; ++l) {
+    if (l > 0 && (rc = upload_layer(h, enc_name(l, 1), chan(l - 1), chan(l), false))) return rc;
+    if ((rc = upload_layer(h, enc_name(l, 2), chan(l), chan(l), false))) return rc;
+  }
+  for (int l = n - 1; l >= 0; --l) {
+    if ((rc = upload_layer(h, up_name(l), chan(l + 1), chan(l), true))) return rc;
+    if ((rc = upload_layer(h, dec_name(l, 1), 2 * chan(l), chan(l), false))) return rc;
+    if ((rc = upload_layer(h, dec_name(l, 2), chan(l), chan(l), false))) return rc;
+  }
+  if ((rc = expect_dims(h, "outconv.weight", {1, 64, 1, 1}, &w))) return rc;
+  if ((rc = expect_dims(h, "outconv.bias", {1}, &b))) return rc;
+  std::memcpy(h->wout, w->data.data(), 64 * 4);
+  h->bout = b->data[0];
+  if (h->plan) { free_plan(h->plan.get()); h->plan.reset(); }  // plans embed wout/bout and weight pointers
+  h->committed = true;
+  return WSU_OK;
+}
+
+int wsu_unet_forward(wsu_handle h, const void* x_dev, int x_dtype, float* y_dev, int B, int H, int W, void* stream) {
+  if (!x_dev || !y_dev) return fail(WSU_ERR_INVALID, "null tensor pointer");
+  return unet_ws_device(h, x_dev, x_dtype, B, H, W, false, 0, 0, 0, nullptr, nullptr, y_dev, static_cast<cudaStream_t>(stream));
+}
+
+int wsu_unet_ws_estimate(wsu_handle h, const void* img_dev, int img_dtype, int B, int H, int W, int weighted, int clip,
+                         int crop, float* beta_dev, float* l1_dev, float* yhat_dev, void* stream) {
+  if (!img_dev || !beta_dev) return fail(WSU_ERR_INVALID, "null tensor pointer");
+  return unet_ws_device(h, img_dev, img_dtype, B, H, W, true, weighted, clip, crop, beta_dev, l1_dev, yhat_dev,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int wsu_unet_ws_estimate_host(wsu_handle h, const uint8_t* img_host, int B, int H, int W, int weighted, int clip, int crop,
+                              float* beta_host, float* l1_host) {
+  if (!h) return fail(WSU_ERR_INVALID, "null handle");
+  if (!img_host || !beta_host) return fail(WSU_ERR_INVALID, "null host pointer");
+  int rc = check_shape(h, B, H, W);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int mb = pick_micro_batch(h, B, H, W);
+  const size_t px = size_t(H) * W;
+  if (!h->s_copy) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->ev_free[i], cudaEventDisableTiming));
+    }
+  }
+  if (h->stage_px < size_t(mb) * px) {
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(h->stage_img[i]);
+      h->stage_img[i] = nullptr;
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->stage_img[i]), size_t(mb) * px));
+    }
+    h->stage_px = size_t(mb) * px;
+  }
+  if (h->stage_imgs < size_t(B)) {
+    cudaFree(h->stage_out);
+    h->stage_out = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->stage_out), size_t(B) * 2 * sizeof(float)));
+    h->stage_imgs = size_t(B);
+  }
+  float* beta_dev = h->stage_out;
+  float* l1_dev = h->stage_out + B;
+  int slot = 0;
+  for (int b0 = 0; b0 < B; b0 += mb, slot ^= 1) {
+    const int nimg = std::min(mb, B - b0);
+    CUDA_TRY(cudaStreamWaitEvent(h->s_copy, h->ev_free[slot], 0));  // slot's previous consumer finished
+    CUDA_TRY(cudaMemcpyAsync(h->stage_img[slot], img_host + size_t(b0) * px, size_t(nimg) * px, cudaMemcpyHostToDevice,
+                             h->s_copy));
+    CUDA_TRY(cudaEventRecord(h->ev_in[slot], h->s_copy));
+    CUDA_TRY(cudaStreamWaitEvent(h->s_comp, h->ev_in[slot], 0));
+    rc = unet_ws_device(h, h->stage_img[slot], WSU_U8, nimg, H, W, true, weighted, clip, crop, beta_dev + b0, l1_dev + b0, nullptr,
+                        h->s_comp);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(h->ev_free[slot], h->s_comp));
+  }
+  CUDA_TRY(cudaMemcpyAsync(beta_host, beta_dev, size_t(B) * 4, cudaMemcpyDeviceToHost, h->s_comp));
+  if (l1_host) CUDA_TRY(cudaMemcpyAsync(l1_host, l1_dev, size_t(B) * 4, cudaMemcpyDeviceToHost, h->s_comp));
+  CUDA_TRY(cudaStreamSynchronize(h->s_comp));
+  return WSU_OK;
+}
+
+int wsu_filter_predict(int device, const void* img_dev, int img_dtype, int kind, float* xhat_dev, int B, int H, int W,
+                       void* stream) {
+  int rc = filter_common_check(img_dev, img_dtype, kind, B, H, W);
+  if (rc) return rc;
+  if (!xhat_dev) return fail(WSU_ERR_INVALID, "null output pointer");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partials = nullptr;
+  const int strips = filter_ws_strips(H);
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partials), size_t(B) * strips * kPartialSlots * 4, st));
+  LAUNCH_TRY(launch_filter_ws(img_dev, img_dtype == WSU_F32, B, H, W, kind, 0, 0, xhat_dev, partials, st));
+  CUDA_TRY(cudaFreeAsync(partials, st));
+  return WSU_OK;
+}
+
+int wsu_filter_ws_estimate(int device, const void* img_dev, int img_dtype, int kind, int weighted, int clip,
+                           int correct_bias, float* beta_dev, float* l1_dev, int B, int H, int W, void* stream) {
+  int rc = filter_common_check(img_dev, img_dtype, kind, B, H, W);
+  if (rc) return rc;
+  if (!beta_dev) return fail(WSU_ERR_INVALID, "null output pointer");
+  if (weighted < -1 || weighted > 1) return fail(WSU_ERR_INVALID, "weighted must be -1, 0 or 1");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partials = nullptr;
+  const int strips = filter_ws_strips(H);
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partials), size_t(B) * strips * kPartialSlots * 4, st));
+  LAUNCH_TRY(launch_filter_ws(img_dev, img_dtype == WSU_F32, B, H, W, kind, weighted, correct_bias, nullptr, partials, st));
+  LAUNCH_TRY(launch_finalize(partials, strips, B, float(H - 2) * float(W - 2), clip, correct_bias, beta_dev, l1_dev, st));
+  CUDA_TRY(cudaFreeAsync(partials, st));
+  return WSU_OK;
+}
+
+int wsu_filter_ws_estimate_host(int device, const uint8_t* img_host, int kind, int weighted, int clip, int correct_bias,
+                                float* beta_host, float* l1_host, int B, int H, int W) {
+  if (!img_host || !beta_host) return fail(WSU_ERR_INVALID, "null host pointer");
+  CUDA_TRY(cudaSetDevice(device));
+  static thread_local cudaStream_t s[2] = {nullptr, nullptr};
+  if (!s[0]) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&s[0], cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s[1], cudaStreamNonBlocking));
+  }
+  const size_t px = size_t(H) * W;
+  // chunks alternate between two streams so the H2D copy of one overlaps the kernel of the other
+  const int chunk = std::max(1, std::min(B, int((size_t(64) << 20) / px)));
+  uint8_t* dimg = nullptr;
+  float* dout = nullptr;
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dimg), size_t(B) * px));
+  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dout), size_t(B) * 2 * 4));
+  int rc = WSU_OK, k = 0;
+  for (int b0 = 0; b0 < B && rc == WSU_OK; b0 += chunk, k ^= 1) {
+    const int n = std::min(chunk, B - b0);
+    cudaError_t e = cudaMemcpyAsync(dimg + size_t(b0) * px, img_host + size_t(b0) * px, size_t(n) * px, cudaMemcpyHostToDevice, s[k]);
+    if (e != cudaSuccess) { rc = fail(WSU_ERR_CUDA, cudaGetErrorString(e)); break; }
+    rc = wsu_filter_ws_estimate(device, dimg + size_t(b0) * px, WSU_U8, kind, weighted, clip, correct_bias, dout + b0,
+                                dout + B + b0, n, H, W, s[k]);
+    if (rc) break;
+    cudaMemcpyAsync(beta_host + b0, dout + b0, size_t(n) * 4, cudaMemcpyDeviceToHost, s[k]);
+    if (l1_host) cudaMemcpyAsync(l1_host + b0, dout + B + b0, size_t(n) * 4, cudaMemcpyDeviceToHost, s[k]);
+  }
+  cudaStreamSynchronize(s[0]);
+  cudaStreamSynchronize(s[1]);
+  cudaFree(dimg);
+  cudaFree(dout);
+  if (rc) return rc;
+  CUDA_TRY(cudaGetLastError());
+  return WSU_OK;
+}
+
+int wsu_ws_from_prediction(int device, const void* img_dev, int img_dtype, const float* xhat_dev, int xhat_cropped,
+                           const float* xbias_dev, int weighted, int clip, int crop, float* beta_dev, float* l1_dev, int B,
+                           int H, int W, void* stream) {
+  if (!img_dev || !xhat_dev || !beta_dev) return fail(WSU_ERR_INVALID, "null tensor pointer");
+  if (img_dtype != WSU_U8 && img_dtype != WSU_F32) return fail(WSU_ERR_INVALID, "dtype must be WSU_U8 or WSU_F32");
+  if (B <= 0 || H < 3 || W < 3) return fail(WSU_ERR_INVALID, "need B >= 1 and H, W >= 3");
+  if (weighted < -1 || weighted > 1) return fail(WSU_ERR_INVALID, "weighted must be -1, 0 or 1");
+  if (weighted != 0 && !crop) return fail(WSU_ERR_INVALID, "local-variance weights exist only on the interior (crop=1)");
+  if (xhat_cropped && !crop) return fail(WSU_ERR_INVALID, "cropped predictions need crop=1");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int chunks = 32;
+  float* partials = nullptr;
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partials), size_t(B) * chunks * kPartialSlots * 4, st));
+  LAUNCH_TRY(launch_ws_from_pred(img_dev, img_dtype == WSU_F32, xhat_dev, xhat_cropped, xbias_dev, B, H, W, weighted, crop,
+                                 partials, chunks, st));
+  const float npix = crop ? float(H - 2) * float(W - 2) : float(H) * float(W);
+  LAUNCH_TRY(launch_finalize(partials, chunks, B, npix, clip, xbias_dev != nullptr, beta_dev, l1_dev, st));
+  CUDA_TRY(cudaFreeAsync(partials, st));
+  return WSU_OK;
+}
+
+int wsu_debug_layer(wsu_handle h, const char* name, float* dst_dev, size_t cap, int with_halo, int64_t* dims_out,
+                    void* stream) {
+  if (!h || !name || !dst_dev) return fail(WSU_ERR_INVALID, "null argument");
+  if (!h->plan) return fail(WSU_ERR_STATE, "no forward pass has run yet");
+  auto it = h->plan->acts.find(name);
+  if (it == h->plan->acts.end()) return fail(WSU_ERR_INVALID, std::string("unknown layer ") + name);
+  const Act& a = it->second;
+  const int Ho = a.H + (with_halo ? 2 : 0), Wo = a.W + (with_halo ? 2 : 0);
+  if (size_t(a.B) * a.C * Ho * Wo > cap) return fail(WSU_ERR_INVALID, "destination too small");
+  if (dims_out) { dims_out[0] = a.B; dims_out[1] = a.C; dims_out[2] = Ho; dims_out[3] = Wo; }
+  CUDA_TRY(cudaSetDevice(h->device));
+  LAUNCH_TRY(launch_unpack(a, dst_dev, with_halo, static_cast<cudaStream_t>(stream)));
+  return WSU_OK;
+}
+
+}  // extern "C"

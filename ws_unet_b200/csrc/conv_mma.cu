@@ -1,0 +1,352 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for the UNet pixel predictor.
+//
+// Replaces (from scratch, B200-native) the reference's nn.Conv2d(3x3, reflect) + F.relu blocks, the
+// nn.ConvTranspose2d(k=2,s=2) up-convolutions, torch.cat skip concatenation, nn.MaxPool2d(2,2) and the
+// 1x1 outconv + sigmoid head of UNet.forward (src/unet/model/unet.py:137-189), and fuses the WS residual
+// reduction of src/unet/evaluate.py:128-132 / src/ws/estimate.py:113-121 into the last layer's epilogue.
+//
+// GEMM view: M = pixels (128-pixel TWxTH boxes), N = Cout tile, K = 64-channel block x tap.
+//   A operand: one 5-D TMA box load {64 ch, TW, TH, 1 img, 2 planes} of the haloed split-bf16 activation at the
+//              tap's offset -> two K-major SWIZZLE_128B tiles (hi, lo) of 128 rows x 128 B.
+//   B operand: pre-swizzled packed weights, one 1-D bulk copy per (tap, channel block) -> (hi, lo) tiles.
+//   D: fp32 in TMEM, M_SUB accumulators per stage (weights are reused across M_SUB pixel boxes), two stages so
+//      the epilogue of tile i overlaps the MMAs of tile i+1.
+//   Precision: D += Ahi*Whi + Alo*Whi + Ahi*Wlo  (3 bf16 MMAs per algorithmic MAC).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue.
+#include "conv_mma.h"
+#include "ptx.cuh"
+#include "ws_math.cuh"
+
+namespace wsu {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kABytes = 2 * 128 * 128;  // hi + lo tile of 128 pixels x 64 channels
+constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
+
+template <int N_TILE>
+struct Cfg {
+  static constexpr int M_SUB = kAccCols / N_TILE;          // pixel boxes sharing one weight chunk
+  static constexpr int W_BYTES = wchunk_bytes(N_TILE);
+  static constexpr int SA = (N_TILE == 64) ? 5 : 4;        // A ring depth
+  static constexpr int SW = (N_TILE == 64) ? 3 : 2;        // W ring depth
+  static constexpr int SMEM = SA * kABytes + SW * W_BYTES + 1024 /*align*/ + 4096 /*bias*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+  int b, y0, x0, nt, pos, tile_in_img;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int idx, int m_sub) {
+  TileCoord t;
+  t.pos = idx % p.npos;
+  idx /= p.npos;
+  t.nt = idx % p.n_tiles;
+  idx /= p.n_tiles;
+  const int tx = idx % p.tiles_x;
+  idx /= p.tiles_x;
+  const int ty = idx % p.tiles_y;
+  t.b = idx / p.tiles_y;
+  t.x0 = tx * p.TW * m_sub;
+  t.y0 = ty * p.TH;
+  t.tile_in_img = ty * p.tiles_x + tx;
+  return t;
+}
+
+// store 32 channels (hi words h[16], lo words l[16]) of one pixel to every halo target of (oy, ox)
+__device__ __forceinline__ void store_pixel32(const Act& o, int b, int oy, int ox, int c0, const uint32_t (&h)[16],
+                                              const uint32_t (&l)[16]) {
+  int ys[3], xs[3];
+  const int ny = halo_targets(oy, o.H, ys);
+  const int nx = halo_targets(ox, o.W, xs);
+  for (int iy = 0; iy < ny; ++iy) {
+    for (int ix = 0; ix < nx; ++ix) {
+      const size_t off = ((size_t(b) * (o.H + 2) + ys[iy]) * (o.W + 2) + xs[ix]) * o.C + c0;
+      uint4* ph = reinterpret_cast<uint4*>(o.base + off);
+      uint4* pl = reinterpret_cast<uint4*>(o.base + o.plane + off);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        ph[q] = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+        pl[q] = make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
+      }
+    }
+  }
+}
+
+template <int N_TILE, int EPI>
+__global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_constant__ ConvParams p) {
+  using C = Cfg<N_TILE>;
+  constexpr int M_SUB = C::M_SUB;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                   // SA x 32 KB
+  uint8_t* sW = smem + C::SA * kABytes;                 // SW x W_BYTES
+  float* sBias = reinterpret_cast<float*>(sW + C::SW * C::W_BYTES);  // up to 1024 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + 4096);
+  uint64_t* a_full = bars;                 // [SA]
+  uint64_t* a_empty = a_full + C::SA;      // [SA]
+  uint64_t* w_full = a_empty + C::SA;      // [SW]
+  uint64_t* w_empty = w_full + C::SW;      // [SW]
+  uint64_t* acc_full = w_empty + C::SW;    // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int KB = p.cblocks * p.ntaps;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmapA0);
+    prefetch_tmap(&p.tmapA1);
+    for (int i = 0; i < C::SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::SW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < p.cout && i < 1024; i += kThreads) sBias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int as = 0, ws = 0;
+      uint32_t aph = 0, wph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, M_SUB);
+        const uint8_t* wsrc = p.wpack + size_t(t.pos * p.n_tiles + t.nt) * KB * C::W_BYTES;
+        for (int kb = 0; kb < KB; ++kb) {
+          const int c = kb / p.ntaps;
+          const int tap = kb - c * p.ntaps;
+          mbar_wait(&w_empty[ws], wph ^ 1);
+          mbar_arrive_expect_tx(&w_full[ws], C::W_BYTES);
+          bulk_load(sW + ws * C::W_BYTES, wsrc + size_t(kb) * C::W_BYTES, C::W_BYTES, &w_full[ws]);
+          if (++ws == C::SW) { ws = 0; wph ^= 1; }
+          const bool src0 = c < p.cblocks0;
+          const CUtensorMap* tm = src0 ? &p.tmapA0 : &p.tmapA1;
+          const int ch = (src0 ? c : c - p.cblocks0) * 64;
+#pragma unroll 1
+          for (int j = 0; j < M_SUB; ++j) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            mbar_arrive_expect_tx(&a_full[as], kABytes);
+            tma_load_5d(sA + as * kABytes, tm, &a_full[as], ch, t.x0 + j * p.TW + p.tap_dx[tap],
+                        t.y0 + p.tap_dy[tap], t.b, 0);
+            if (++as == C::SA) { as = 0; aph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(N_TILE);
+      int as = 0, ws = 0, acs = 0;
+      uint32_t aph = 0, wph = 0, acph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acs], acph ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&w_full[ws], wph);
+          const uint32_t w_hi = smem_u32(sW + ws * C::W_BYTES);
+          const uint32_t w_lo = w_hi + N_TILE * 128;
+#pragma unroll 1
+          for (int j = 0; j < M_SUB; ++j) {
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(sA + as * kABytes);
+            const uint32_t a_lo = a_hi + 128 * 128;
+            const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * N_TILE);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da_hi = make_sw128_desc(a_hi + k * 32);
+              const uint64_t da_lo = make_sw128_desc(a_lo + k * 32);
+              const uint64_t dw_hi = make_sw128_desc(w_hi + k * 32);
+              const uint64_t dw_lo = make_sw128_desc(w_lo + k * 32);
+              umma_bf16(d, da_hi, dw_hi, idesc, (kb | k) != 0);
+              umma_bf16(d, da_lo, dw_hi, idesc, 1);
+              umma_bf16(d, da_hi, dw_lo, idesc, 1);
+            }
+            umma_commit(&a_empty[as]);  // frees the A slot when these MMAs retire
+            if (++as == C::SA) { as = 0; aph ^= 1; }
+          }
+          umma_commit(&w_empty[ws]);
+          if (++ws == C::SW) { ws = 0; wph ^= 1; }
+        }
+        umma_commit(&acc_full[acs]);
+        if (++acs == 2) { acs = 0; acph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (TMEM -> registers -> HBM)
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;           // pixel row of the 128-pixel box
+    const int ty = row / p.TW, tx = row - ty * p.TW;
+    int acs = 0;
+    uint32_t acph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile, M_SUB);
+      mbar_wait(&acc_full[acs], acph);
+      tc_fence_after();
+      const int y = t.y0 + ty;
+      WsAcc acc;
+#pragma unroll 1
+      for (int j = 0; j < M_SUB; ++j) {
+        const int x = t.x0 + j * p.TW + tx;
+        const bool valid = (y < p.H) && (x < p.W);
+        const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acs * kAccCols + j * N_TILE);
+        if constexpr (EPI == EPI_ACT) {
+#pragma unroll 1
+          for (int cc = 0; cc < N_TILE / 32; ++cc) {
+            uint32_t v[32];
+            tmem_ld32(tbase + cc * 32, v);
+            tmem_ld_wait();
+            const int n0 = t.nt * N_TILE + cc * 32;
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              f[i] = __uint_as_float(v[i]) + sBias[n0 + i];
+              if (p.relu) f[i] = fmaxf(f[i], 0.f);
+            }
+            uint32_t h[16], l[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
+            if (valid) {
+              const int oy = p.upsample ? 2 * y + (t.pos >> 1) : y;
+              const int ox = p.upsample ? 2 * x + (t.pos & 1) : x;
+              store_pixel32(p.out, t.b, oy, ox, n0, h, l);
+            }
+            if (p.do_pool) {
+              // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
+                f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 16));
+              }
+              if (valid && !(tx & 1) && !(ty & 1)) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
+                store_pixel32(p.pool, t.b, y >> 1, x >> 1, n0, h, l);
+              }
+            }
+          }
+        } else {
+          // 1x1 outconv over the 64 ReLU'd channels of d42, sigmoid, WS residual terms
+          float z = p.bout;
+#pragma unroll 1
+          for (int cc = 0; cc < N_TILE / 32; ++cc) {
+            uint32_t v[32];
+            tmem_ld32(tbase + cc * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float a = fmaxf(__uint_as_float(v[i]) + sBias[cc * 32 + i], 0.f);
+              z = fmaf(a, p.wout[cc * 32 + i], z);
+            }
+          }
+          if (valid) {
+            const float s = 1.f / (1.f + expf(-z));
+            const size_t pix = (size_t(t.b) * p.H + y) * p.W + x;
+            if (p.yhat) p.yhat[pix] = s;
+            const bool inside = p.crop ? (y >= 1 && y < p.H - 1 && x >= 1 && x < p.W - 1) : true;
+            if (p.img && inside) {
+              const float xhat = s * 255.f;
+              float xv, xbar, s1 = 0.f, s2 = 0.f;
+              if (p.img_is_float) {
+                const float* im = static_cast<const float*>(p.img);
+                ws_load_f32(im[pix], xv, xbar);
+                if (p.weighted != WS_UNWEIGHTED) {
+                  for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                      if (dy == 0 && dx == 0) continue;
+                      const float q = im[pix + dy * p.W + dx] * 255.f;
+                      s1 += q;
+                      s2 = fmaf(q, q, s2);
+                    }
+                }
+              } else {
+                const uint8_t* im = static_cast<const uint8_t*>(p.img);
+                ws_load_u8(im[pix], xv, xbar);
+                if (p.weighted != WS_UNWEIGHTED) {
+                  int i1 = 0, i2 = 0;
+                  for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                      if (dy == 0 && dx == 0) continue;
+                      const int q = im[pix + dy * p.W + dx];
+                      i1 += q;
+                      i2 += q * q;
+                    }
+                  s1 = float(i1);
+                  s2 = float(i2);
+                }
+              }
+              ws_accumulate(acc, xv, xbar, xhat, ws_weight(p.weighted, s1, s2));
+            }
+          }
+        }
+      }
+      // all TMEM reads of this stage are complete -> hand the accumulators back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acs]);
+      if (++acs == 2) { acs = 0; acph ^= 1; }
+      if constexpr (EPI == EPI_HEAD) {
+        if (p.partials) {
+          const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1);
+          if (lane == 0) {
+            const size_t tiles_per_img = size_t(p.tiles_x) * p.tiles_y;
+            float* dst = p.partials + ((size_t(t.b) * tiles_per_img + t.tile_in_img) * 4 + quad) * kPartialSlots;
+            dst[0] = wr;
+            dst[1] = w;
+            dst[2] = l1;
+            dst[3] = 0.f;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int N_TILE, int EPI>
+cudaError_t launch_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  conv_mma_kernel<N_TILE, EPI><<<grid, kThreads, Cfg<N_TILE>::SMEM, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t conv_mma_init() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(conv_mma_kernel<64, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_mma_kernel<128, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_mma_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM);
+  return e;
+}
+
+cudaError_t launch_conv_mma(const ConvParams& p, int n_tile, int epi, int num_sms, cudaStream_t stream) {
+  if (p.TW * p.TH != 128) return cudaErrorInvalidValue;
+  if (p.do_pool && p.TW != 16) return cudaErrorInvalidValue;
+  if (epi == EPI_HEAD) {
+    if (n_tile != 64 || p.n_tiles != 1) return cudaErrorInvalidValue;
+    return launch_t<64, EPI_HEAD>(p, num_sms, stream);
+  }
+  if (n_tile == 64) return launch_t<64, EPI_ACT>(p, num_sms, stream);
+  if (n_tile == 128) return launch_t<128, EPI_ACT>(p, num_sms, stream);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace wsu

@@ -1,0 +1,52 @@
+// Parameter block + host launcher of the tcgen05 implicit-GEMM convolution (conv_mma.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "wsu_common.cuh"
+
+namespace wsu {
+
+enum : int { EPI_ACT = 0, EPI_HEAD = 1 };
+
+// One launch = one layer of UNet.forward (src/unet/model/unet.py:141-189) over a micro-batch.
+struct alignas(64) ConvParams {
+  CUtensorMap tmapA0;  // first concat source  (upsampled path, unet.py:178 puts it first)
+  CUtensorMap tmapA1;  // second concat source (skip); unused when cblocks == cblocks0
+  const uint8_t* wpack;  // packed + pre-swizzled split-bf16 weights, see pack_conv_weights()
+  const float* bias;     // [Cout]
+  int cblocks0;          // 64-channel blocks taken from source 0
+  int cblocks;           // total 64-channel blocks (K = 64 * cblocks * ntaps)
+  int ntaps;             // 9 (3x3 conv) or 1 (one phase of the 2x2 stride-2 transposed conv)
+  int tap_dx[9], tap_dy[9];  // tap offsets in padded (halo) coordinates
+  int npos;              // 1, or 4 output phases for the transposed conv
+  int n_tiles;           // Cout / N_TILE
+  int cout;              // Cout
+  int B, H, W;           // logical input dims (= GEMM pixel grid)
+  int TW, TH;            // sub-tile box (TW*TH == 128 pixels)
+  int tiles_x, tiles_y;  // super-tiles (M_SUB sub-tiles side by side in x) per image
+  int total_tiles;
+  // EPI_ACT
+  int relu;
+  int upsample;          // 1: write phase (pos>>1, pos&1) of a 2x upsampled map (ConvTranspose2d k=2,s=2)
+  Act out;               // destination (dims = output dims)
+  int do_pool;           // also write MaxPool2d(2,2) of the output (unet.py:144,149); needs TW == 16
+  Act pool;
+  // EPI_HEAD: 1x1 outconv + sigmoid (unet.py:189) and the WS reduction
+  const void* img;       // [B][H][W] uint8 or float32 pixels the residual is taken against (may be null)
+  int img_is_float;
+  float wout[64];
+  float bout;
+  float* yhat;           // [B][H][W] sigmoid output in (0,1), may be null
+  float* partials;       // [B][tiles_per_img][4 warps][kPartialSlots]
+  int weighted;          // WS_* mode
+  int crop;              // 1: interior only (estimate.py:113-114), 0: whole image (losses.py:57-60)
+};
+
+// Bytes of one packed weight chunk (hi + lo tile) for an N_TILE-wide tile and one 64-deep K block.
+constexpr int wchunk_bytes(int n_tile) { return n_tile * 64 * 2 * 2; }
+
+cudaError_t launch_conv_mma(const ConvParams& p, int n_tile, int epi, int num_sms, cudaStream_t stream);
+cudaError_t conv_mma_init();  // sets max dynamic shared memory on every instantiation
+
+}  // namespace wsu

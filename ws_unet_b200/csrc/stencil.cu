@@ -1,0 +1,376 @@
+// CUDA-core kernels of the hot path: everything that is HBM-bound rather than tensor-bound.
+//   * first_conv_kernel   - e11 (Cin = in_channels, K = 9*Cin, src/unet/model/unet.py:82,141): reads the image
+//                           (uint8 pixels -> x/255 as src/unet/evaluate.py:45, or float [0,1]) and writes the
+//                           split-bf16 NHWC activation with its reflect halo.
+//   * filter_ws_kernel    - KB / AVG / AVG9 / identity predictor (src/filters/evaluate.py:29-50,136-141) fused with
+//                           the WS estimator (src/ws/estimate.py:83-128): LSB flip, residual, local-variance
+//                           weights, per-image partial sums. One pass over the uint8 image: 1 B/pixel read.
+//   * ws_from_pred_kernel - WS reduction against a caller-supplied x_hat (second pass of correct_bias, or any
+//                           external predictor output).
+//   * finalize_kernel     - deterministic fixed-order reduction of the partial sums to beta_hat / l1 per image.
+//   * pack / unpack       - NCHW fp32 <-> split-bf16 NHWC, used by the per-layer parity tests.
+#include "stencil.h"
+#include "ws_math.cuh"
+
+namespace wsu {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ e11
+// 8 threads per pixel, 8 output channels each: a warp writes 4 adjacent pixels = 512 contiguous bytes per plane.
+template <bool kFloatIn>
+__global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict__ img, int cin, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, Act out) {
+  extern __shared__ float sw[];  // [64][cin*9] + [64] bias
+  const int kk = cin * 9;
+  for (int i = threadIdx.x; i < 64 * kk; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) sw[64 * kk + i] = bias[i];
+  __syncthreads();
+  const int H = out.H, W = out.W;
+  const size_t npix = size_t(out.B) * H * W;
+  const size_t gid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t pix = gid >> 3;
+  if (pix >= npix) return;
+  const int cg = int(gid & 7);  // channel group
+  const int x = int(pix % W);
+  const int y = int((pix / W) % H);
+  const int b = int(pix / (size_t(W) * H));
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = sw[64 * kk + cg * 8 + i];
+  for (int ci = 0; ci < cin; ++ci) {
+    float in[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      int yy = y + dy - 1;
+      yy = yy < 0 ? -yy : (yy >= H ? 2 * H - 2 - yy : yy);  // reflect (unet.py:73)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        int xx = x + dx - 1;
+        xx = xx < 0 ? -xx : (xx >= W ? 2 * W - 2 - xx : xx);
+        const size_t o = ((size_t(b) * cin + ci) * H + yy) * W + xx;
+        if constexpr (kFloatIn) {
+          in[dy * 3 + dx] = static_cast<const float*>(img)[o];
+        } else {
+          in[dy * 3 + dx] = __fdiv_rn(float(static_cast<const uint8_t*>(img)[o]), 255.f);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* wr = &sw[(cg * 8 + i) * kk + ci * 9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[i] = fmaf(in[t], wr[t], acc[i]);
+    }
+  }
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_pack2(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f), h[i], l[i]);
+  int ys[3], xs[3];
+  const int ny = halo_targets(y, H, ys), nx = halo_targets(x, W, xs);
+  for (int iy = 0; iy < ny; ++iy)
+    for (int ix = 0; ix < nx; ++ix) {
+      const size_t off = ((size_t(b) * (H + 2) + ys[iy]) * (W + 2) + xs[ix]) * out.C + cg * 8;
+      *reinterpret_cast<uint4*>(out.base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint4*>(out.base + out.plane + off) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ filter WS
+// One CTA = one (image, 8-row strip). 128 threads x 4 pixels = one 512-pixel row segment per row; wider images loop.
+// The strip and its +-1 rows are staged in shared memory with 16-byte loads where alignment allows.
+constexpr int kStripRows = 8;
+constexpr int kFThreads = 256;
+
+__device__ __forceinline__ float predict_linear(int kind, const float (&n)[9]) {
+  // n = 3x3 neighbourhood row-major, n[4] = centre. All sums of <= 9 uint8 values are exact in fp32.
+  const float cross = (n[1] + n[3]) + (n[5] + n[7]);
+  const float diag = (n[0] + n[2]) + (n[6] + n[8]);
+  switch (kind) {
+    case PRED_KB: return (2.f * cross - diag) * 0.25f;           // [[-1,2,-1],[2,0,2],[-1,2,-1]]/4
+    case PRED_AVG: return (cross + diag) * 0.125f;               // 8 neighbours / 8
+    case PRED_AVG9: return __fdiv_rn((cross + diag) + n[4], 9.f);  // 3x3 box / 9
+    default: return n[4];                                        // '1'
+  }
+}
+
+template <bool kFloatIn>
+__global__ void __launch_bounds__(kFThreads) filter_ws_kernel(const void* __restrict__ img, int B, int H, int W, int kind,
+                                                              int weighted, int want_bias, float* __restrict__ xhat_out,
+                                                              float* __restrict__ partials, int strips) {
+  extern __shared__ float tile[];  // (kStripRows + 2) x (W) pixel values as float
+  const int b = blockIdx.x / strips;
+  const int strip = blockIdx.x - b * strips;
+  const int y0 = 1 + strip * kStripRows;               // first interior row of this strip
+  const int rows = min(kStripRows, (H - 1) - y0);      // interior rows y0 .. y0+rows-1
+  const int lrows = rows + 2;
+  // stage rows y0-1 .. y0+rows
+  if constexpr (kFloatIn) {
+    const float* src = static_cast<const float*>(img) + (size_t(b) * H + (y0 - 1)) * W;
+    for (int i = threadIdx.x; i < lrows * W; i += kFThreads) tile[i] = src[i] * 255.f;
+  } else {
+    const uint8_t* src = static_cast<const uint8_t*>(img) + (size_t(b) * H + (y0 - 1)) * W;
+    const int total = lrows * W;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const int nvec = total >> 4;
+      const uint4* s4 = reinterpret_cast<const uint4*>(src);
+      for (int i = threadIdx.x; i < nvec; i += kFThreads) {
+        const uint4 v = __ldg(s4 + i);
+        const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tile[i * 16 + q * 4 + k] = float((wds[q] >> (8 * k)) & 0xffu);
+      }
+      for (int i = (nvec << 4) + threadIdx.x; i < total; i += kFThreads) tile[i] = float(src[i]);
+    } else {
+      for (int i = threadIdx.x; i < total; i += kFThreads) tile[i] = float(src[i]);
+    }
+  }
+  __syncthreads();
+
+  WsAcc acc;
+  const int wi = W - 2;  // interior width
+  for (int i = threadIdx.x; i < rows * wi; i += kFThreads) {
+    const int r = i / wi;
+    const int x = 1 + (i - r * wi);
+    const float* c = tile + (r + 1) * W + x;
+    float n[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) n[dy * 3 + dx] = c[(dy - 1) * W + (dx - 1)];
+    const float xv = n[4];
+    const float xbar = float(__float2int_rn(xv) ^ 1);
+    const float xhat = predict_linear(kind, n);
+    float s1 = 0.f, s2 = 0.f;
+    if (weighted != WS_UNWEIGHTED) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        if (k != 4) {
+          s1 += n[k];
+          s2 = fmaf(n[k], n[k], s2);
+        }
+    }
+    const float wgt = ws_weight(weighted, s1, s2);
+    ws_accumulate(acc, xv, xbar, xhat, wgt);
+    if (want_bias) {
+      // predictor applied to the difference image x_bar - x (estimate.py:127); linear => apply to parities
+      float dn[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) dn[k] = float(__float2int_rn(n[k]) ^ 1) - n[k];
+      const float xb = predict_linear(kind, dn);
+      acc.wb = fmaf(wgt * (xv - xbar), xb, acc.wb);
+    }
+    if (xhat_out) xhat_out[(size_t(b) * (H - 2) + (y0 - 1 + r)) * wi + (x - 1)] = xhat;
+  }
+  // block reduce in fixed order: warp shuffles, then warp 0 sums the 8 warp results sequentially
+  __shared__ float red[kFThreads / 32][kPartialSlots];
+  const float v0 = warp_sum(acc.wr), v1 = warp_sum(acc.w), v2 = warp_sum(acc.l1), v3 = warp_sum(acc.wb);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[warp][0] = v0;
+    red[warp][1] = v1;
+    red[warp][2] = v2;
+    red[warp][3] = v3;
+  }
+  __syncthreads();
+  if (threadIdx.x < kPartialSlots) {
+    float s = 0.f;
+    for (int wv = 0; wv < kFThreads / 32; ++wv) s += red[wv][threadIdx.x];
+    partials[(size_t(b) * strips + strip) * kPartialSlots + threadIdx.x] = s;
+  }
+}
+
+// WS terms against a caller-supplied prediction (pixel units), grid-stride per image chunk.
+template <bool kFloatIn>
+__global__ void __launch_bounds__(256) ws_from_pred_kernel(const void* __restrict__ img, const float* __restrict__ xhat,
+                                                           int xhat_cropped, const float* __restrict__ xbias, int B, int H,
+                                                           int W, int weighted, int crop, float* __restrict__ partials,
+                                                           int chunks) {
+  const int b = blockIdx.x / chunks;
+  const int chunk = blockIdx.x - b * chunks;
+  const int h = crop ? H - 2 : H, w = crop ? W - 2 : W;
+  const int npix = h * w;
+  const int per = (npix + chunks - 1) / chunks;
+  const int lo = chunk * per, hi = min(npix, lo + per);
+  WsAcc acc;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) {
+    const int r = i / w, cidx = i - r * w;
+    const int y = r + crop, x = cidx + crop;
+    const size_t pix = (size_t(b) * H + y) * W + x;
+    float xv, xbar, s1 = 0.f, s2 = 0.f;
+    if constexpr (kFloatIn) {
+      const float* im = static_cast<const float*>(img);
+      ws_load_f32(im[pix], xv, xbar);
+      if (weighted != WS_UNWEIGHTED)
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            if (!dy && !dx) continue;
+            const float q = im[pix + dy * W + dx] * 255.f;
+            s1 += q;
+            s2 = fmaf(q, q, s2);
+          }
+    } else {
+      const uint8_t* im = static_cast<const uint8_t*>(img);
+      ws_load_u8(im[pix], xv, xbar);
+      if (weighted != WS_UNWEIGHTED) {
+        int i1 = 0, i2 = 0;
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            if (!dy && !dx) continue;
+            const int q = im[pix + dy * W + dx];
+            i1 += q;
+            i2 += q * q;
+          }
+        s1 = float(i1);
+        s2 = float(i2);
+      }
+    }
+    const size_t pidx = xhat_cropped ? (size_t(b) * (H - 2) + (y - 1)) * (W - 2) + (x - 1) : pix;
+    const float wgt = ws_weight(weighted, s1, s2);
+    ws_accumulate(acc, xv, xbar, xhat[pidx], wgt);
+    if (xbias) acc.wb = fmaf(wgt * (xv - xbar), xbias[pidx], acc.wb);
+  }
+  __shared__ float red[8][kPartialSlots];
+  const float v0 = warp_sum(acc.wr), v1 = warp_sum(acc.w), v2 = warp_sum(acc.l1), v3 = warp_sum(acc.wb);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[warp][0] = v0;
+    red[warp][1] = v1;
+    red[warp][2] = v2;
+    red[warp][3] = v3;
+  }
+  __syncthreads();
+  if (threadIdx.x < kPartialSlots) {
+    float s = 0.f;
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][threadIdx.x];
+    partials[(size_t(b) * chunks + chunk) * kPartialSlots + threadIdx.x] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+// One warp per image; partial records are summed in double in a fixed order => beta_hat is bit-reproducible
+// across runs, batch composition and GPU count.
+__global__ void finalize_kernel(const float* __restrict__ partials, int records, int B, float npix, int clip,
+                                int correct_bias, float* __restrict__ beta_hat, float* __restrict__ l1) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int lane = threadIdx.x & 31;
+  double s[kPartialSlots] = {0, 0, 0, 0};
+  const float* src = partials + size_t(b) * records * kPartialSlots;
+  for (int r = lane; r < records; r += 32)
+    for (int k = 0; k < kPartialSlots; ++k) s[k] += double(src[r * kPartialSlots + k]);
+  for (int k = 0; k < kPartialSlots; ++k)
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+  if (lane == 0) {
+    float beta = float(s[0] / s[1]);
+    if (clip) beta = fmaxf(beta, 0.f);
+    if (correct_bias) beta -= beta * float(s[3] / s[1]);  // estimate.py:128
+    beta_hat[b] = beta;
+    if (l1) l1[b] = float(s[2] / double(npix));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ debug pack/unpack
+__global__ void pack_kernel(const float* __restrict__ src, Act dst) {
+  const size_t n = size_t(dst.B) * dst.C * dst.H * dst.W;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const int c = int(i % dst.C);
+    const int x = int((i / dst.C) % dst.W);
+    const int y = int((i / (size_t(dst.C) * dst.W)) % dst.H);
+    const int b = int(i / (size_t(dst.C) * dst.W * dst.H));
+    const float v = src[((size_t(b) * dst.C + c) * dst.H + y) * dst.W + x];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    int ys[3], xs[3];
+    const int ny = halo_targets(y, dst.H, ys), nx = halo_targets(x, dst.W, xs);
+    for (int iy = 0; iy < ny; ++iy)
+      for (int ix = 0; ix < nx; ++ix) {
+        const size_t off = ((size_t(b) * (dst.H + 2) + ys[iy]) * (dst.W + 2) + xs[ix]) * dst.C + c;
+        dst.base[off] = h;
+        dst.base[dst.plane + off] = l;
+      }
+  }
+}
+
+// with_halo: dst is (B,C,H+2,W+2) and receives the stored border too (lets tests check the reflect halo)
+__global__ void unpack_kernel(Act src, float* __restrict__ dst, int with_halo) {
+  const int Ho = src.H + (with_halo ? 2 : 0), Wo = src.W + (with_halo ? 2 : 0);
+  const size_t n = size_t(src.B) * src.C * Ho * Wo;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const int x = int(i % Wo);
+    const int y = int((i / Wo) % Ho);
+    const int c = int((i / (size_t(Wo) * Ho)) % src.C);
+    const int b = int(i / (size_t(Wo) * Ho * src.C));
+    const int sy = with_halo ? y : y + 1, sx = with_halo ? x : x + 1;
+    const size_t off = ((size_t(b) * (src.H + 2) + sy) * (src.W + 2) + sx) * src.C + c;
+    dst[i] = __bfloat162float(src.base[off]) + __bfloat162float(src.base[src.plane + off]);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_first_conv(const void* img, int img_is_float, int cin, const float* w, const float* bias, Act out,
+                              cudaStream_t stream) {
+  const size_t threads = size_t(out.B) * out.H * out.W * 8;
+  const int grid = int((threads + 255) / 256);
+  const size_t smem = (64 * cin * 9 + 64) * sizeof(float);
+  if (img_is_float)
+    first_conv_kernel<true><<<grid, 256, smem, stream>>>(img, cin, w, bias, out);
+  else
+    first_conv_kernel<false><<<grid, 256, smem, stream>>>(img, cin, w, bias, out);
+  return cudaGetLastError();
+}
+
+int filter_ws_strips(int H) { return (H - 2 + kStripRows - 1) / kStripRows; }
+
+cudaError_t launch_filter_ws(const void* img, int img_is_float, int B, int H, int W, int kind, int weighted, int want_bias,
+                             float* xhat_out, float* partials, cudaStream_t stream) {
+  const int strips = filter_ws_strips(H);
+  const size_t smem = size_t(kStripRows + 2) * W * sizeof(float);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  if (img_is_float) {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(filter_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    filter_ws_kernel<true><<<B * strips, kFThreads, smem, stream>>>(img, B, H, W, kind, weighted, want_bias, xhat_out,
+                                                                    partials, strips);
+  } else {
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(filter_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    filter_ws_kernel<false><<<B * strips, kFThreads, smem, stream>>>(img, B, H, W, kind, weighted, want_bias, xhat_out,
+                                                                     partials, strips);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ws_from_pred(const void* img, int img_is_float, const float* xhat, int xhat_cropped, const float* xbias,
+                                int B, int H, int W, int weighted, int crop, float* partials, int chunks,
+                                cudaStream_t stream) {
+  if (img_is_float)
+    ws_from_pred_kernel<true><<<B * chunks, 256, 0, stream>>>(img, xhat, xhat_cropped, xbias, B, H, W, weighted, crop,
+                                                              partials, chunks);
+  else
+    ws_from_pred_kernel<false><<<B * chunks, 256, 0, stream>>>(img, xhat, xhat_cropped, xbias, B, H, W, weighted, crop,
+                                                               partials, chunks);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(const float* partials, int records, int B, float npix, int clip, int correct_bias,
+                            float* beta_hat, float* l1, cudaStream_t stream) {
+  const int warps_per_block = 4;
+  finalize_kernel<<<(B + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
+      partials, records, B, npix, clip, correct_bias, beta_hat, l1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const float* src, Act dst, cudaStream_t stream) {
+  pack_kernel<<<1024, 256, 0, stream>>>(src, dst);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack(Act src, float* dst, int with_halo, cudaStream_t stream) {
+  unpack_kernel<<<1024, 256, 0, stream>>>(src, dst, with_halo);
+  return cudaGetLastError();
+}
+
+}  // namespace wsu

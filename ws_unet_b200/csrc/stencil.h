@@ -1,0 +1,21 @@
+// Host launchers of the CUDA-core kernels in stencil.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "wsu_common.cuh"
+
+namespace wsu {
+
+cudaError_t launch_first_conv(const void* img, int img_is_float, int cin, const float* w, const float* bias, Act out,
+                              cudaStream_t stream);
+int filter_ws_strips(int H);
+cudaError_t launch_filter_ws(const void* img, int img_is_float, int B, int H, int W, int kind, int weighted, int want_bias,
+                             float* xhat_out, float* partials, cudaStream_t stream);
+cudaError_t launch_ws_from_pred(const void* img, int img_is_float, const float* xhat, int xhat_cropped, const float* xbias,
+                                int B, int H, int W, int weighted, int crop, float* partials, int chunks,
+                                cudaStream_t stream);
+cudaError_t launch_finalize(const float* partials, int records, int B, float npix, int clip, int correct_bias,
+                            float* beta_hat, float* l1, cudaStream_t stream);
+cudaError_t launch_pack(const float* src, Act dst, cudaStream_t stream);
+cudaError_t launch_unpack(Act src, float* dst, int with_halo, cudaStream_t stream);
+
+}  // namespace wsu

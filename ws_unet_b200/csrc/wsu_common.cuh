@@ -1,0 +1,58 @@
+// Shared device/host definitions for the UNet -> WS hot path.
+//
+// Activation layout in HBM ("split-bf16 NHWC with reflect halo"):
+//   every feature map of the reference's UNet.forward (src/unet/model/unet.py:137-189) is stored as TWO bf16
+//   planes hi = bf16(v), lo = bf16(v - hi) (hi + lo carries 16 significand bits of the fp32 value), each laid
+//   out [B][H+2][W+2][C] with the 1-pixel reflect border of padding_mode='reflect' (unet.py:73) materialised by
+//   the producing kernel. A 3x3 tap is then a plain in-bounds TMA box load and the convolution is
+//   hi*Whi + lo*Whi + hi*Wlo on the bf16 tensor cores with fp32 accumulation in TMEM.
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace wsu {
+
+struct Act {
+  __nv_bfloat16* base;  // plane 0 (hi); plane 1 (lo) starts at base + plane
+  size_t plane;         // elements per plane = B*(H+2)*(W+2)*C
+  int B, H, W, C;
+};
+
+__host__ __device__ inline size_t act_plane_elems(int B, int H, int W, int C) {
+  return size_t(B) * size_t(H + 2) * size_t(W + 2) * size_t(C);
+}
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// pack two floats as hi-parts / lo-parts bf16x2 words (element 0 in the low half).
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  __nv_bfloat16 ah, al, bh, bl;
+  split_bf16(a, ah, al);
+  split_bf16(b, bh, bl);
+  hi2 = uint32_t(__bfloat16_as_ushort(ah)) | (uint32_t(__bfloat16_as_ushort(bh)) << 16);
+  lo2 = uint32_t(__bfloat16_as_ushort(al)) | (uint32_t(__bfloat16_as_ushort(bl)) << 16);
+}
+
+// Reflect-halo targets of a logical coordinate v in [0,n): storage index v+1, plus the mirrored border
+// rows/cols it also owns (index 0 mirrors logical 1, index n+1 mirrors logical n-2).
+__device__ __forceinline__ int halo_targets(int v, int n, int (&t)[3]) {
+  int k = 0;
+  t[k++] = v + 1;
+  if (v == 1) t[k++] = 0;
+  if (v == n - 2) t[k++] = n + 1;
+  return k;
+}
+
+// WS estimator modes (src/ws/estimate.py:55-136)
+enum : int { WS_UNWEIGHTED = 0, WS_WEIGHTED = 1, WS_ANTIWEIGHTED = -1 };
+// linear predictors (src/ws/estimate.py:31-52, src/filters/evaluate.py:29-50)
+enum : int { PRED_KB = 0, PRED_AVG = 1, PRED_AVG9 = 2, PRED_ID = 3 };
+
+// number of float slots per partial-sum record: sum(w*r), sum(w), sum|x-xhat|, sum(w*d*xbias)
+constexpr int kPartialSlots = 4;
+
+}  // namespace wsu

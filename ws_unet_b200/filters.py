@@ -1,0 +1,77 @@
+"""Linear pixel predictors (KB, AVG, AVG9, identity) - drop-in for src/filters/evaluate.py:22-50,118-146.
+
+`get_filter_estimator(name, flatten=False)` returns the same kind of callable the reference returns:
+(H,W,C>=1) float32 pixels -> (H-2,W-2,1) float32 pixels, computed by libwsunet's stencil kernel on the GPU
+(exact fp32 integer arithmetic instead of the reference's FFT path).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+
+# coefficient tables kept for callers that read them (src/filters/evaluate.py:22-50)
+NAMED_FILTERS = {
+    'KB': np.array([[-1], [+2], [-1], [+2], [-1], [+2], [-1], [+2]], dtype='float64') / 4.,
+    'AVG': np.ones((8, 1)) / 8.,
+}
+NAMED_FILTERS_2D = {
+    'KB': np.array([[[-1, +2, -1], [+2, 0, +2], [-1, +2, -1]]], dtype='float32').T / 4.,
+    'AVG': np.array([[[1, 1, 1], [1, 0, 1], [1, 1, 1]]], dtype='float32').T / 8.,
+    'AVG9': np.array([[[1, 1, 1], [1, 1, 1], [1, 1, 1]]], dtype='float32').T / 9.,
+    '1': np.array([[[0, 0, 0], [0, 1, 0], [0, 0, 0]]], dtype='float32').T / 1.,
+}
+
+
+def get_coefficients(filter_name: str, flatten: bool = True) -> np.ndarray:
+    return NAMED_FILTERS[filter_name] if flatten else NAMED_FILTERS_2D[filter_name]
+
+
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("ws_unet_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def filter_predict(images: torch.Tensor, filter_name: str) -> torch.Tensor:
+    """Batched predictor: images (B,H,W) or (B,1,H,W), uint8 pixels or float32 in [0,1], on a CUDA device
+    -> (B,H-2,W-2) float32 predictions in pixel units."""
+    if filter_name not in _native.PRED_KINDS:
+        raise KeyError(filter_name)
+    if not images.is_cuda:
+        raise RuntimeError("images must live on a CUDA device")
+    if images.dim() == 4:
+        images = images[:, 0]
+    dtype = _native.WSU_U8 if images.dtype == torch.uint8 else _native.WSU_F32
+    if dtype == _native.WSU_F32:
+        images = images.to(torch.float32)
+    images = images.contiguous()
+    B, H, W = images.shape
+    out = torch.empty((B, H - 2, W - 2), dtype=torch.float32, device=images.device)
+    with torch.cuda.device(images.device):
+        _native.check(_native.load().wsu_filter_predict(
+            images.device.index, ctypes.c_void_p(images.data_ptr()), dtype, _native.PRED_KINDS[filter_name],
+            ctypes.c_void_p(out.data_ptr()), B, H, W, _native.stream_ptr(images.device)), 'wsu_filter_predict')
+    return out
+
+
+def infere_single(x: np.ndarray, filter_name: str, device=None) -> np.ndarray:
+    """src/filters/evaluate.py:136-141: (H,W,C) float32 pixel units -> (H-2,W-2,1). Non-integer inputs (e.g. the
+    +-1 difference image of estimate.py:127) go through the float path: the kernel sees x/255 like the reference."""
+    dev = _device(device)
+    x0 = np.ascontiguousarray(np.asarray(x)[..., 0], dtype=np.float32)
+    t = torch.from_numpy(x0 / np.float32(255.)).to(dev)[None]
+    y = filter_predict(t, filter_name)[0]
+    return y.cpu().numpy()[..., None]
+
+
+def get_filter_estimator(filter_name: str, flatten: bool = False, device=None):
+    """src/filters/evaluate.py:144-146."""
+    if flatten:
+        raise NotImplementedError("flatten=True is the matrix-form OLS path (filters/evaluate.py:53-76), not the hot path")
+    if filter_name not in NAMED_FILTERS_2D:
+        raise KeyError(filter_name)
+    return lambda x: infere_single(x, filter_name, device)

@@ -1,0 +1,181 @@
+"""B200-native drop-in for the reference's UNet pixel predictor.
+
+Mirrors the interface of src/unet/model/unet.py:54-199 (class UNet) and src/unet/model/__init__.py:8-49
+(get_model): same constructor arguments, same sub-module names and construction order (so
+`torch.manual_seed(s); get_model(...)` draws the same initial weights and `state_dict()` /
+`load_state_dict()` are interchangeable with the reference), `to()` returning self,
+`disable_center_pixels()`, `input_dropout` attribute. `forward` does not run PyTorch layers: it hands the
+weights and the input to libwsunet (tcgen05 implicit-GEMM convolutions) through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+from torch import nn
+
+from .. import _native
+
+
+class UniformDropout(nn.Module):
+    """Input dropout of the reference (unet.py:15-51). With drop_rate=0 (every shipped inference path,
+    src/unet/evaluate.py:175-181) the keep-probability is 1 and the layer is the identity, so it is elided.
+    drop_rate>0 is a training-time feature and is not implemented."""
+
+    def __init__(self, p: float, drop_channel):
+        super().__init__()
+        self.p = 1 - p
+        self.drop_channel = drop_channel
+
+    def forward(self, x):
+        if self.p != 1:
+            raise NotImplementedError("UniformDropout with drop_rate>0 is training-only and not implemented")
+        return x
+
+
+class UNet(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int, nsteps: int, drop_rate: float, drop_channel):
+        super().__init__()
+        assert nsteps >= 0
+        if nsteps > 4:
+            raise NotImplementedError("nsteps > 4")
+        self.nsteps = nsteps
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        conv_kw = {'kernel_size': 3, 'padding': 1, 'padding_mode': 'reflect'}
+        ups_kw = {'kernel_size': 2, 'stride': 2}
+        # same order as unet.py:78-135 so parameter initialisation consumes the RNG identically
+        if drop_rate is not None:
+            self.input_dropout = UniformDropout(p=drop_rate, drop_channel=drop_channel)
+        else:
+            self.input_dropout = None
+        self.e11 = nn.Conv2d(in_channels, 64, **conv_kw)
+        self.e12 = nn.Conv2d(64, 64, **conv_kw)
+        if nsteps >= 1:
+            self.e21 = nn.Conv2d(64, 128, **conv_kw)
+            self.e22 = nn.Conv2d(128, 128, **conv_kw)
+        if nsteps >= 2:
+            self.e31 = nn.Conv2d(128, 256, **conv_kw)
+            self.e32 = nn.Conv2d(256, 256, **conv_kw)
+        if nsteps >= 3:
+            self.e41 = nn.Conv2d(256, 512, **conv_kw)
+            self.e42 = nn.Conv2d(512, 512, **conv_kw)
+        if nsteps >= 4:
+            self.e51 = nn.Conv2d(512, 1024, **conv_kw)
+            self.e52 = nn.Conv2d(1024, 1024, **conv_kw)
+        if nsteps >= 4:
+            self.upconv1 = nn.ConvTranspose2d(1024, 512, **ups_kw)
+            self.d11 = nn.Conv2d(1024, 512, **conv_kw)
+            self.d12 = nn.Conv2d(512, 512, **conv_kw)
+        if nsteps >= 3:
+            self.upconv2 = nn.ConvTranspose2d(512, 256, **ups_kw)
+            self.d21 = nn.Conv2d(512, 256, **conv_kw)
+            self.d22 = nn.Conv2d(256, 256, **conv_kw)
+        if nsteps >= 2:
+            self.upconv3 = nn.ConvTranspose2d(256, 128, **ups_kw)
+            self.d31 = nn.Conv2d(256, 128, **conv_kw)
+            self.d32 = nn.Conv2d(128, 128, **conv_kw)
+        if nsteps >= 1:
+            self.upconv4 = nn.ConvTranspose2d(128, 64, **ups_kw)
+            self.d41 = nn.Conv2d(128, 64, **conv_kw)
+            self.d42 = nn.Conv2d(64, 64, **conv_kw)
+        self.outconv = nn.Conv2d(64, out_channels, kernel_size=1, padding_mode='reflect')
+        self._handle = None       # wsu_handle (ctypes.c_void_p)
+        self._handle_device = None
+        self._weights_key = None
+
+    # ------------------------------------------------------------------ native handle management
+    def __getstate__(self):  # joblib workers pickle the model (src/ws/estimate.py:139-146)
+        state = self.__dict__.copy()
+        state['_handle'] = None
+        state['_handle_device'] = None
+        state['_weights_key'] = None
+        return state
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _release(self):
+        if getattr(self, '_handle', None) is not None:
+            _native.load().wsu_destroy(self._handle)
+            self._handle = None
+
+    def _key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def native_handle(self, device: torch.device):
+        """Create (once per device) the libwsunet context and keep its packed weights in sync with the
+        module's parameters (load_state_dict / in-place edits bump tensor versions)."""
+        lib = _native.load()
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        if self._handle is None or self._handle_device != dev_index:
+            self._release()
+            h = ctypes.c_void_p()
+            _native.check(lib.wsu_create(ctypes.byref(h), dev_index, self.nsteps, self.in_channels, self.out_channels),
+                          'wsu_create')
+            self._handle, self._handle_device, self._weights_key = h, dev_index, None
+        key = self._key()
+        if key != self._weights_key:
+            for name, t in self.state_dict().items():
+                host = t.detach().to('cpu', torch.float32).contiguous()
+                dims = (ctypes.c_int64 * host.dim())(*host.shape)
+                _native.check(lib.wsu_load_weights(self._handle, name.encode(), ctypes.c_void_p(host.data_ptr()), dims,
+                                                   host.dim()), f'wsu_load_weights({name})')
+            _native.check(lib.wsu_commit_weights(self._handle), 'wsu_commit_weights')
+            self._weights_key = key
+        return self._handle
+
+    # ------------------------------------------------------------------ reference interface
+    def forward(self, x_in: torch.Tensor) -> torch.Tensor:
+        if self.input_dropout is not None:
+            x_in = self.input_dropout(x_in)
+        if not x_in.is_cuda:
+            raise RuntimeError("ws_unet_b200.UNet runs on a B200 only: move the input to a CUDA device "
+                               "(there is no CPU fallback)")
+        if x_in.dim() != 4 or x_in.shape[1] != self.in_channels:
+            raise RuntimeError(f"expected input (B,{self.in_channels},H,W), got {tuple(x_in.shape)}")
+        if x_in.dtype == torch.uint8:
+            dtype = _native.WSU_U8
+        else:
+            dtype = _native.WSU_F32
+            x_in = x_in.to(torch.float32)
+        x_in = x_in.contiguous()
+        B, _, H, W = x_in.shape
+        if H % (1 << self.nsteps) or W % (1 << self.nsteps):
+            # the reference fails inside torch.cat with a RuntimeError (unet.py:178)
+            raise RuntimeError(f"Sizes of tensors must match: H={H}, W={W} not divisible by {1 << self.nsteps}")
+        h = self.native_handle(x_in.device)
+        y = torch.empty((B, 1, H, W), dtype=torch.float32, device=x_in.device)
+        with torch.cuda.device(x_in.device):
+            _native.check(_native.load().wsu_unet_forward(h, ctypes.c_void_p(x_in.data_ptr()), dtype,
+                                                          ctypes.c_void_p(y.data_ptr()), B, H, W,
+                                                          _native.stream_ptr(x_in.device)), 'wsu_unet_forward')
+        return y
+
+    def to(self, *args, **kw):
+        super().to(*args, **kw)
+        if self.input_dropout is not None:
+            self.input_dropout.to(*args, **kw)
+        return self
+
+    def disable_center_pixels(self):
+        self.e11.weight.data[:, :, 1, 1] = 0.
+        if self.e11.weight.grad is not None:
+            self.e11.weight.grad[:, :, 1, 1] = 0.
+
+    def set_micro_batch(self, n: int, device=None):
+        """Images per pass through the layer chain (0 = auto from free HBM budget)."""
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        _native.check(_native.load().wsu_set_option(self.native_handle(dev), b'micro_batch', int(n)))
+
+
+def get_model(name: str, in_channels: int, out_channels: int = 1, channel=[0], drop_rate: float = 0.) -> nn.Module:
+    """src/unet/model/__init__.py:8-49."""
+    if name.lower().startswith('unet'):
+        nsteps = int(name.split('_')[1])
+        return UNet(in_channels=in_channels, out_channels=out_channels, nsteps=nsteps, drop_channel=channel,
+                    drop_rate=drop_rate)
+    raise NotImplementedError(name)

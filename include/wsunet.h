@@ -52,7 +52,8 @@ int wsu_destroy(wsu_handle h);
 int wsu_load_weights(wsu_handle h, const char* name, const float* data, const int64_t* dims, int ndims);
 int wsu_commit_weights(wsu_handle h);
 
-/* options: "micro_batch" (images per pass through the layer chain; 0 = auto) */
+/* options: "micro_batch" (images per pass through the layer chain; 0 = auto);
+ *          "profile" (1: record CUDA events around every layer launch of the last micro-batch) */
 int wsu_set_option(wsu_handle h, const char* key, int64_t value);
 
 /* UNet.forward (src/unet/model/unet.py:137-189): x_dev (B,in_channels,H,W) in [0,1] as float32, or uint8 pixels
@@ -96,6 +97,13 @@ int wsu_ws_from_prediction(int device, const void* img_dev, int img_dtype, const
  * (B,C,H+2,W+2) including the materialised reflect border. dims_out receives (B,C,H,W) of the returned tensor. */
 int wsu_debug_layer(wsu_handle h, const char* name, float* dst_dev, size_t dst_capacity_elems, int with_halo,
                     int64_t* dims_out, void* stream);
+/* introspection: "micro_batch" (images per pass of the current plan), "last_images" (images in the last pass that ran),
+ * "num_sms", "layers" (kernel launches per pass) */
+int wsu_get_info(wsu_handle h, const char* key, int64_t* out);
+/* per-layer device times (ms) of the last micro-batch when option "profile" is on; returns the layer count (>= 0)
+ * or a negative status. wsu_profile_name(i) names entry i ("e11", "e12", ..., "d42"). */
+int wsu_profile_read(wsu_handle h, float* ms_out, int cap);
+const char* wsu_profile_name(wsu_handle h, int i);
 /* number of kernels launched by this library in the calling thread since the last call (bench.py gpu_launches) */
 int64_t wsu_launch_count(int reset);
 

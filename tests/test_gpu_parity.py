@@ -1,0 +1,259 @@
+"""GPU (B200): parity of the CUDA path, called through the C ABI, against (i) golden outputs of the unmodified
+reference, (ii) the CPU oracle on seeded inputs, (iii) size-independent properties at BASELINE.json sizes.
+
+Tolerances are BASELINE.json's: LSB/parity/integer handling bit-exact, predictions <= 1e-3 px max-abs,
+beta_hat <= 1e-4 absolute.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ATTACK_MODES, GOLDEN_UNET_CASES
+from oracle import unet_oracle as uo
+from oracle import ws_oracle as wo
+
+pytestmark = pytest.mark.gpu
+PX_TOL = 1e-3
+BETA_TOL = 1e-4
+
+
+def _model(nsteps, seed, dev):
+    import ws_unet_b200 as W
+    m = W.get_model(f'unet_{nsteps}', 1).to(dev)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in uo.numpy_weights(nsteps, seed=seed).items()})
+    return m
+
+
+def test_native_library_is_the_path(cuda_dev):
+    """The product path is libwsunet: a forward pass must launch its kernels (no eager-PyTorch fallback)."""
+    from ws_unet_b200 import _native
+    m = _model(2, 1, cuda_dev)
+    _native.load().wsu_launch_count(1)
+    m(torch.rand(1, 1, 32, 32, device=cuda_dev))
+    assert _native.load().wsu_launch_count(0) == 1 + 11  # e11 + 11 tensor-core layers (e12..e32, upconv3, d31, d32, upconv4, d41, d42)
+
+
+# ------------------------------------------------------------------------------------------------ UNet forward
+@pytest.mark.parametrize('nsteps,h,w', GOLDEN_UNET_CASES)
+def test_unet_forward_matches_reference_golden(cuda_dev, unet_golden, nsteps, h, w):
+    m = _model(nsteps, 100 + nsteps, cuda_dev)
+    x, y_ref = unet_golden[f'unet{nsteps}_{h}x{w}_x'], unet_golden[f'unet{nsteps}_{h}x{w}_y']
+    y = m(torch.from_numpy(x).to(cuda_dev)).cpu().numpy()
+    assert y.shape == y_ref.shape
+    assert np.abs(y - y_ref).max() * 255 < PX_TOL
+
+
+@pytest.mark.parametrize('nsteps,b,h,w', [(2, 1, 8, 8), (2, 3, 72, 40), (2, 2, 128, 200), (1, 5, 34, 66), (3, 1, 16, 152)])
+def test_unet_forward_matches_oracle_ragged(cuda_dev, nsteps, b, h, w):
+    """Ragged / non-square / minimum sizes: tiles overhang the image, reflect border at every level."""
+    sd = uo.numpy_weights(nsteps, seed=7)
+    m = _model(nsteps, 7, cuda_dev)
+    x = np.random.default_rng(h * 1000 + w).random((b, 1, h, w), dtype=np.float32)
+    y = m(torch.from_numpy(x).to(cuda_dev)).cpu().numpy()
+    y_ref, acts = uo.unet_forward(sd, x, nsteps, keep=True)
+    assert np.abs(y - y_ref).max() * 255 < PX_TOL
+
+
+def test_unet_layers_and_reflect_halo_match_oracle(cuda_dev):
+    from ws_unet_b200 import _native
+    sd = uo.numpy_weights(2, seed=9)
+    m = _model(2, 9, cuda_dev)
+    x = np.random.default_rng(3).random((2, 1, 48, 80), dtype=np.float32)
+    m(torch.from_numpy(x).to(cuda_dev))
+    _, acts = uo.unet_forward(sd, x, 2, keep=True)
+    lib = _native.load()
+    for name in ['e11', 'e12', 'p1', 'e21', 'e22', 'p2', 'e31', 'e32', 'u3', 'd31', 'd32', 'u4', 'd41']:
+        ref = acts[name]
+        ref_h = np.pad(ref, ((0, 0), (0, 0), (1, 1), (1, 1)), mode='reflect')
+        dims = (ctypes.c_int64 * 4)()
+        buf = torch.empty(ref_h.size, dtype=torch.float32, device=cuda_dev)
+        _native.check(lib.wsu_debug_layer(m._handle, name.encode(), ctypes.c_void_p(buf.data_ptr()), buf.numel(), 1, dims,
+                                          _native.stream_ptr(cuda_dev)))
+        got = buf.view(*ref_h.shape).cpu().numpy()
+        assert tuple(dims) == ref_h.shape
+        assert np.abs(got - ref_h).max() < 2e-5 * max(1.0, np.abs(ref).max()), name
+
+
+def test_unet_uint8_input_equals_float_input(cuda_dev):
+    m = _model(2, 11, cuda_dev)
+    img = torch.randint(0, 256, (2, 1, 64, 64), dtype=torch.uint8, device=cuda_dev)
+    y8 = m(img)
+    yf = m(img.float() / 255.)
+    assert torch.equal(y8, yf)  # x/255 is the same IEEE division on both paths (src/unet/evaluate.py:45)
+
+
+def test_unet_shape_errors(cuda_dev):
+    m = _model(2, 1, cuda_dev)
+    with pytest.raises(RuntimeError):
+        m(torch.rand(1, 1, 510, 510, device=cuda_dev))  # reference: torch.cat size mismatch
+    with pytest.raises(RuntimeError):
+        m(torch.rand(1, 2, 64, 64, device=cuda_dev))
+
+
+# ------------------------------------------------------------------------------------------------ fused UNet -> WS
+def test_unet_ws_512_matches_reference_golden(cuda_dev, unet_golden):
+    import ws_unet_b200 as W
+    from ws_unet_b200 import data as wdata
+    m = _model(2, 102, cuda_dev)
+    stego = wdata.embed_lsbr(wdata.synthetic_cover(0), 0.4, 0)
+    img = stego[None, None].to(cuda_dev)
+    beta, l1, yhat = W.ws_estimate(img, m, weighted=0, clip=False, crop=1, return_l1=True, return_prediction=True)
+    xhat = (yhat[0, 0, 1:-1, 1:-1] * 255.).cpu().numpy()
+    assert np.abs(xhat[::7, ::7] - unet_golden['unet2_512_xhat_sub']).max() < PX_TOL     # infere_single
+    assert abs(beta.item() - unet_golden['unet2_512_beta_l1'][0]) < BETA_TOL               # predict_unet beta_hat
+    assert abs(l1.item() - unet_golden['unet2_512_beta_l1'][1]) < 1e-3                     # predict_unet l1
+    ref = unet_golden['unet2_512_attack_w0_w1_wm1_w1bias']
+    for i, (weighted, bias) in enumerate([(0, False), (1, False), (-1, False), (1, True)]):
+        got = W.ws_estimate(img, m, weighted=weighted, clip=True, crop=1, correct_bias=bias).item()
+        assert abs(got - ref[i]) < BETA_TOL, (weighted, bias, got, ref[i])
+
+
+def test_unet_ws_matches_oracle_batch(cuda_dev):
+    import ws_unet_b200 as W
+    from ws_unet_b200 import data as wdata
+    sd = uo.numpy_weights(2, seed=5)
+    m = _model(2, 5, cuda_dev)
+    imgs = torch.stack([wdata.embed_lsbr(wdata.synthetic_cover(i, 96, 128), a, i) for i, a in enumerate([0.0, 0.05, 0.4, 1.0])])[:, None]
+    d = imgs.to(cuda_dev)
+    for weighted, clip in [(0, False), (0, True), (1, True), (-1, True)]:
+        beta, l1 = W.ws_estimate(d, m, weighted=weighted, clip=clip, crop=1, return_l1=True)
+        for i in range(imgs.shape[0]):
+            im = imgs[i, 0].numpy()
+            xhat = uo.unet_forward(sd, (im.astype(np.float32) / np.float32(255.))[None, None], 2)[0, 0, 1:-1, 1:-1] * np.float32(255.)
+            b_ref, l_ref, _ = uo.ws_attack_c(im, xhat=xhat, weighted=weighted, clip=clip)
+            assert abs(beta[i].item() - b_ref) < BETA_TOL, (weighted, clip, i)
+            assert abs(l1[i].item() - l_ref) < 1e-3
+
+
+def test_unet_ws_whole_image_float_matches_wsloss(cuda_dev, ws_golden):
+    """crop=0 on float images = WSLoss._error betas_hat (src/_defs/losses.py:46-61) with the UNet as predictor."""
+    import ws_unet_b200 as W
+    m = _model(2, 21, cuda_dev)
+    xin = torch.from_numpy(ws_golden['wsloss_xin']).to(cuda_dev)
+    beta, yhat = W.ws_estimate(xin, m, weighted=0, clip=True, crop=0, return_prediction=True)
+    ref = wo.wsloss_betas(yhat.cpu().numpy(), ws_golden['wsloss_xin'], crop=0)
+    assert np.abs(beta.cpu().numpy() - ref).max() < BETA_TOL
+
+
+# ------------------------------------------------------------------------------------------------ linear filters
+@pytest.mark.parametrize('tag', ['cover', 'lsbr04', 'lsbr10', 'hill04'])
+@pytest.mark.parametrize('name', ['KB', 'AVG', 'AVG9', '1'])
+def test_filter_predict_and_ws_match_reference_golden(cuda_dev, ws_golden, tag, name):
+    import ws_unet_b200 as W
+    img = ws_golden[f'img_{tag}']
+    d = torch.from_numpy(img)[None, None].to(cuda_dev)
+    pred = W.filters.filter_predict(d, name)[0].cpu().numpy()
+    assert np.abs(pred - ws_golden[f'pred_{tag}_{name}']).max() < PX_TOL
+    assert np.abs(pred - wo.filter_predict_exact(img[..., None], name)[..., 0]).max() < 2e-5   # exact stencil
+    # reference-style callable: (H,W,C) float32 -> (H-2,W-2,1)
+    est = W.filters.get_filter_estimator(name)
+    y = est(img[..., None].astype(np.float32))
+    assert y.shape == (img.shape[0] - 2, img.shape[1] - 2, 1) and y.dtype == np.float32
+    assert np.abs(y[..., 0] - ws_golden[f'pred_{tag}_{name}']).max() < PX_TOL
+    ref = ws_golden[f'beta_{tag}_{name}']
+    for i, (weighted, bias) in enumerate(ATTACK_MODES):
+        got = W.ws_estimate(d, name, weighted=weighted, clip=True, correct_bias=bias).item()
+        assert abs(got - ref[i]) < BETA_TOL, (weighted, bias, got, ref[i])
+
+
+def test_attack_signature_and_external_estimator(cuda_dev, ws_golden):
+    """attack() with the reference's argument list; a reference-style callable as pixel_estimator goes through
+    wsu_ws_from_prediction, a filter name through the fused kernel; both must agree with the golden value."""
+    import ws_unet_b200 as W
+    img = ws_golden['img_lsbr04']
+    x4 = np.repeat(img[..., None], 4, axis=2)
+    proc = lambda x: x[..., (3,)].astype('float32')
+    kw = dict(channels=(3,), imread=lambda f: x4, process_image=proc, alpha=0.4)
+    ref = ws_golden['beta_lsbr04_KB']
+    for i, (weighted, bias) in enumerate(ATTACK_MODES):
+        r1 = W.attack('mem', pixel_estimator='KB', weighted=weighted, correct_bias=bias, **kw)
+        r2 = W.attack('mem', pixel_estimator=W.filters.get_filter_estimator('KB'), weighted=weighted, correct_bias=bias, **kw)
+        assert set(r1) == {'alpha', 'beta_hat', 'channels', 'weighted', 'correct_bias'} and r1['channels'] == '3'
+        assert isinstance(r1['beta_hat'], np.float32)
+        assert abs(r1['beta_hat'] - ref[i]) < BETA_TOL and abs(r2['beta_hat'] - ref[i]) < BETA_TOL
+
+
+def test_filter_float_input_and_edge_sizes(cuda_dev):
+    import ws_unet_b200 as W
+    rng = np.random.default_rng(0)
+    for h, w in [(3, 3), (3, 17), (9, 4), (35, 515), (130, 1031)]:
+        img = rng.integers(0, 256, (2, 1, h, w), dtype=np.uint8)
+        d = torch.from_numpy(img).to(cuda_dev)
+        for name in ['KB', 'AVG']:
+            p8 = W.filters.filter_predict(d, name)
+            pf = W.filters.filter_predict(d.float() / 255., name)
+            assert p8.shape == (2, h - 2, w - 2)
+            for i in range(2):
+                ex = wo.filter_predict_exact(img[i, 0][..., None], name)[..., 0]
+                assert np.abs(p8[i].cpu().numpy() - ex).max() < 2e-5
+                assert np.abs(pf[i].cpu().numpy() - ex).max() < 2e-4
+            for weighted in (0, 1, -1):
+                beta = W.ws_estimate(d, name, weighted=weighted, clip=False)
+                for i in range(2):
+                    assert abs(beta[i].item() - uo.ws_attack_c(img[i, 0], kind={'KB': 0, 'AVG': 1}[name], weighted=weighted, clip=False)[0]) < BETA_TOL
+
+
+# ------------------------------------------------------------------------------------------------ bit-exact integer handling
+def test_lsb_flip_and_parity_bit_exact(cuda_dev):
+    """With x_hat = 0 the estimator returns mean((x - x_bar) * x) = mean(+-x): pure integer arithmetic, so the
+    result must equal the exactly computed value bit for bit; with x_hat = x it must be exactly 0."""
+    import ws_unet_b200 as W
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (3, 1, 96, 160), dtype=np.uint8)
+    img[0] = np.arange(96 * 160).reshape(96, 160) % 256          # every pixel value incl. 0/1 and 254/255 pairs
+    d = torch.from_numpy(img).to(cuda_dev)
+    zeros = torch.zeros(3, 96, 160, device=cuda_dev)
+    beta = W.ws_from_prediction(d, zeros, weighted=0, clip=False, crop=1).cpu().numpy()
+    xi = img[:, 0, 1:-1, 1:-1].astype(np.int64)
+    sign = 2 * (xi & 1) - 1                                       # x - (x ^ 1)
+    exact = (sign * xi).sum(axis=(1, 2)) / float(xi[0].size)
+    assert np.array_equal(beta, exact.astype(np.float32))
+    same = W.ws_from_prediction(d, d[:, 0].float(), weighted=0, clip=False, crop=1, return_l1=True)
+    assert torch.all(same[0] == 0) and torch.all(same[1] == 0)
+    assert torch.all(W.ws_estimate(d, '1', weighted=1, clip=False) == 0)   # identity predictor => residual 0
+
+
+# ------------------------------------------------------------------------------------------------ properties at full size
+def test_full_size_properties_512(cuda_dev):
+    """BASELINE config 3 shape (512x512, alpha sweep) through properties: order/batch invariance (bit-exact),
+    idempotence, micro-batch independence, beta_hat tracking alpha/2 for the KB predictor."""
+    import ws_unet_b200 as W
+    from ws_unet_b200 import data as wdata
+    alphas = [0.01, 0.05, 0.1, 0.2, 0.4, 1.0]
+    covers = wdata.synthetic_covers(6)
+    stego = torch.stack([wdata.embed_lsbr(covers[i, 0], a, i) for i, a in enumerate(alphas)])[:, None].to(cuda_dev)
+    kb = W.ws_estimate(stego, 'KB', weighted=0).cpu().numpy()
+    for a, b in zip(alphas, kb):
+        assert abs(b - a / 2) < 0.02, (a, b)                      # KB-WS tracks alpha/2 on this generator
+    m = _model(2, 102, cuda_dev)
+    big = stego.repeat(6, 1, 1, 1)                                # 36 images
+    b1, l1 = W.ws_estimate(big, m, weighted=0, clip=False, return_l1=True)
+    b2 = W.ws_estimate(big, m, weighted=0, clip=False)
+    assert torch.equal(b1, b2)                                    # idempotent / deterministic reduction
+    assert torch.equal(b1[:6], b1[6:12]) and torch.equal(b1[:6], b1[30:])   # position in the batch is irrelevant
+    perm = torch.randperm(36, generator=torch.Generator().manual_seed(0)).to(cuda_dev)
+    assert torch.equal(W.ws_estimate(big[perm], m, weighted=0, clip=False), b1[perm])
+    m.set_micro_batch(5, cuda_dev)                                # ragged micro-batches: 36 = 7*5 + 1
+    assert torch.equal(W.ws_estimate(big, m, weighted=0, clip=False), b1)
+    m.set_micro_batch(0, cuda_dev)
+    # logical 2-way shard (what 2 GPUs would compute) equals the single-GPU vector bit for bit
+    from ws_unet_b200.parallel import shard_range
+    parts = [W.ws_estimate(big[slice(*shard_range(36, r, 2))], m, weighted=0, clip=False) for r in range(2)]
+    assert torch.equal(torch.cat(parts), b1)
+
+
+def test_unet_1024_matches_oracle_strip(cuda_dev):
+    """BASELINE config 5 shape (1024x1024): full forward on the GPU, oracle on one image (CPU cost ~2 min is too
+    much), so compare against the PyTorch-free C oracle on a 1024x64 strip-free subproblem instead: a 64x1024 image
+    exercises the same tile geometry in x (64 super-tiles at level 0)."""
+    sd = uo.numpy_weights(2, seed=13)
+    m = _model(2, 13, cuda_dev)
+    x = np.random.default_rng(5).random((1, 1, 64, 1024), dtype=np.float32)
+    y = m(torch.from_numpy(x).to(cuda_dev)).cpu().numpy()
+    assert np.abs(y - uo.unet_forward(sd, x, 2)).max() * 255 < PX_TOL
+    big = torch.rand(2, 1, 1024, 1024, device=cuda_dev)
+    yb = m(big)
+    assert yb.shape == (2, 1, 1024, 1024) and torch.isfinite(yb).all()
+    assert torch.equal(yb[:1], m(big[:1]))                        # batch independence at full size

@@ -10,7 +10,7 @@ import torch
 sys.path.insert(0, '.')
 import ws_unet_b200 as W
 from ws_unet_b200 import _native
-from tools.torch_ref import reference_forward
+from oracle.torch_port import reference_forward
 
 
 def debug_layer(model, name, dev, halo=0):

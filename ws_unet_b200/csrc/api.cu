@@ -109,6 +109,7 @@ struct Plan {  // everything that depends on (micro-batch, H, W)
   float* partials = nullptr;
   int tiles_per_img = 0;
   std::vector<std::pair<ConvParams, std::pair<int, int>>> convs;  // params, (n_tile, epi); head is the last entry
+  std::vector<std::string> conv_names;
 };
 
 }  // namespace
@@ -130,6 +131,12 @@ struct wsu_context {
   size_t stage_imgs = 0, stage_px = 0;
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  // optional per-layer timing of the last micro-batch ("profile" option)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<std::string> prof_names;
+  int prof_n = 0;
+  int last_nimg = 0;  // images in the last micro-batch that ran
 };
 
 namespace {
@@ -178,7 +185,7 @@ size_t per_image_bytes(int nsteps, int H, int W) {
 }
 
 // Build a conv step. src1 may be null (no concat).
-int add_conv(wsu_context* h, Plan& pl, const LayerW& lw, const Act& src0, const Act* src1, const Act* out, const Act* pool,
+int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& lw, const Act& src0, const Act* src1, const Act* out, const Act* pool,
              bool upsample, bool relu, int epi) {
   ConvParams p;
   std::memset(&p, 0, sizeof(p));
@@ -215,6 +222,7 @@ int add_conv(wsu_context* h, Plan& pl, const LayerW& lw, const Act& src0, const 
     pl.tiles_per_img = p.tiles_x * p.tiles_y;
   }
   pl.convs.push_back({p, {lw.n_tile, epi}});
+  pl.conv_names.push_back(lname);
   return WSU_OK;
 }
 
@@ -249,16 +257,16 @@ int build_plan(wsu_context* h, int mb, int H, int W) {
   auto A = [&](const std::string& s) -> Act& { return pl.acts.at(s); };
   for (int l = 0; l <= n; ++l) {
     if (l > 0) {
-      if ((rc = add_conv(h, pl, h->layers.at(enc_name(l, 1)), A("p" + std::to_string(l)), nullptr, &A(enc_name(l, 1)), nullptr,
+      if ((rc = add_conv(h, pl, enc_name(l, 1), h->layers.at(enc_name(l, 1)), A("p" + std::to_string(l)), nullptr, &A(enc_name(l, 1)), nullptr,
                          false, true, EPI_ACT)))
         return rc;
     }
     if (n == 0) {
-      if ((rc = add_conv(h, pl, h->layers.at(enc_name(0, 2)), A(enc_name(0, 1)), nullptr, nullptr, nullptr, false, true, EPI_HEAD)))
+      if ((rc = add_conv(h, pl, enc_name(0, 2), h->layers.at(enc_name(0, 2)), A(enc_name(0, 1)), nullptr, nullptr, nullptr, false, true, EPI_HEAD)))
         return rc;
     } else {
       const Act* pool = (l < n) ? &A("p" + std::to_string(l + 1)) : nullptr;
-      if ((rc = add_conv(h, pl, h->layers.at(enc_name(l, 2)), A(enc_name(l, 1)), nullptr, &A(enc_name(l, 2)), pool, false, true,
+      if ((rc = add_conv(h, pl, enc_name(l, 2), h->layers.at(enc_name(l, 2)), A(enc_name(l, 1)), nullptr, &A(enc_name(l, 2)), pool, false, true,
                          EPI_ACT)))
         return rc;
     }
@@ -266,16 +274,16 @@ int build_plan(wsu_context* h, int mb, int H, int W) {
   for (int l = n - 1; l >= 0; --l) {
     const std::string below = (l + 1 == n) ? enc_name(l + 1, 2) : dec_name(l + 1, 2);
     const std::string u = "u" + std::to_string(4 - l);
-    if ((rc = add_conv(h, pl, h->layers.at(up_name(l)), A(below), nullptr, &A(u), nullptr, true, false, EPI_ACT))) return rc;
-    if ((rc = add_conv(h, pl, h->layers.at(dec_name(l, 1)), A(u), &A(enc_name(l, 2)), &A(dec_name(l, 1)), nullptr, false, true,
+    if ((rc = add_conv(h, pl, up_name(l), h->layers.at(up_name(l)), A(below), nullptr, &A(u), nullptr, true, false, EPI_ACT))) return rc;
+    if ((rc = add_conv(h, pl, dec_name(l, 1), h->layers.at(dec_name(l, 1)), A(u), &A(enc_name(l, 2)), &A(dec_name(l, 1)), nullptr, false, true,
                        EPI_ACT)))
       return rc;
     if (l > 0) {
-      if ((rc = add_conv(h, pl, h->layers.at(dec_name(l, 2)), A(dec_name(l, 1)), nullptr, &A(dec_name(l, 2)), nullptr, false, true,
+      if ((rc = add_conv(h, pl, dec_name(l, 2), h->layers.at(dec_name(l, 2)), A(dec_name(l, 1)), nullptr, &A(dec_name(l, 2)), nullptr, false, true,
                          EPI_ACT)))
         return rc;
     } else {
-      if ((rc = add_conv(h, pl, h->layers.at(dec_name(l, 2)), A(dec_name(l, 1)), nullptr, nullptr, nullptr, false, true, EPI_HEAD)))
+      if ((rc = add_conv(h, pl, dec_name(l, 2), h->layers.at(dec_name(l, 2)), A(dec_name(l, 1)), nullptr, nullptr, nullptr, false, true, EPI_HEAD)))
         return rc;
     }
   }
@@ -300,15 +308,33 @@ int pick_micro_batch(wsu_context* h, int B, int H, int W) {
   if (h->micro_batch > 0) return int(std::min<int64_t>(h->micro_batch, B));
   const size_t budget = size_t(20) << 30;
   int mb = int(std::max<size_t>(1, budget / per_image_bytes(h->nsteps, H, W)));
-  mb = std::min(mb, 64);
-  return std::min(mb, B);
+  mb = std::min(std::min(mb, 64), B);
+  // even passes: avoid a short ragged tail pass (e.g. B=256 -> 8 x 32 instead of 7 x 33 + 25)
+  const int passes = (B + mb - 1) / mb;
+  return (B + passes - 1) / passes;
 }
 
 // one micro-batch through the layer chain. img points at this micro-batch's first image.
 int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const void* ws_img, int ws_dtype, float* yhat,
               int weighted, int crop, cudaStream_t st) {
   Plan& pl = *h->plan;
+  h->last_nimg = nimg;
   Act first = pl.acts.at(enc_name(0, 1));
+  auto mark = [&](size_t i) {
+    if (!h->profile) return;
+    while (h->prof_ev.size() <= i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      h->prof_ev.push_back(e);
+    }
+    cudaEventRecord(h->prof_ev[i], st);
+  };
+  if (h->profile) {
+    h->prof_names.assign(1, enc_name(0, 1));
+    h->prof_names.insert(h->prof_names.end(), pl.conv_names.begin(), pl.conv_names.end());
+    h->prof_n = int(h->prof_names.size());
+  }
+  mark(0);
   // a short last micro-batch reuses the plan: only the first `nimg` images of each buffer are live
   LAUNCH_TRY(launch_first_conv(img, img_dtype == WSU_F32, h->in_ch, h->e11_w, h->e11_b,
                                Act{first.base, first.plane, nimg, first.H, first.W, first.C}, st));
@@ -327,8 +353,10 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
       p.weighted = weighted;
       p.crop = crop;
     }
+    mark(i + 1);
     LAUNCH_TRY(launch_conv_mma(p, n_tile, epi, h->num_sms, st));
   }
+  mark(pl.convs.size() + 1);
   return WSU_OK;
 }
 
@@ -427,6 +455,7 @@ int wsu_destroy(wsu_handle h) {
     if (h->ev_free[i]) cudaEventDestroy(h->ev_free[i]);
   }
   cudaFree(h->stage_out);
+  for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_comp) cudaStreamDestroy(h->s_comp);
   delete h;
@@ -438,6 +467,10 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
   if (!std::strcmp(key, "micro_batch")) {
     if (value < 0) return fail(WSU_ERR_INVALID, "micro_batch must be >= 0");
     h->micro_batch = value;
+    return WSU_OK;
+  }
+  if (!std::strcmp(key, "profile")) {
+    h->profile = value != 0;
     return WSU_OK;
   }
   return fail(WSU_ERR_INVALID, std::string("unknown option ") + key);
@@ -705,6 +738,31 @@ int wsu_ws_from_prediction(int device, const void* img_dev, int img_dtype, const
   LAUNCH_TRY(launch_finalize(partials, chunks, B, npix, clip, xbias_dev != nullptr, beta_dev, l1_dev, st));
   CUDA_TRY(cudaFreeAsync(partials, st));
   return WSU_OK;
+}
+
+int wsu_get_info(wsu_handle h, const char* key, int64_t* out) {
+  if (!h || !key || !out) return fail(WSU_ERR_INVALID, "null argument");
+  if (!std::strcmp(key, "micro_batch")) *out = h->plan ? h->plan->mb : 0;
+  else if (!std::strcmp(key, "last_images")) *out = h->last_nimg;
+  else if (!std::strcmp(key, "num_sms")) *out = h->num_sms;
+  else if (!std::strcmp(key, "layers")) *out = h->plan ? int64_t(h->plan->convs.size()) + 1 : 0;
+  else return fail(WSU_ERR_INVALID, std::string("unknown info key ") + key);
+  return WSU_OK;
+}
+
+int wsu_profile_read(wsu_handle h, float* ms_out, int cap) {
+  if (!h || !ms_out) return fail(WSU_ERR_INVALID, "null argument");
+  if (!h->profile || h->prof_n == 0 || int(h->prof_ev.size()) < h->prof_n + 1) return fail(WSU_ERR_STATE, "no profile recorded");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaEventSynchronize(h->prof_ev[h->prof_n]));
+  const int n = std::min(cap, h->prof_n);
+  for (int i = 0; i < n; ++i) CUDA_TRY(cudaEventElapsedTime(&ms_out[i], h->prof_ev[i], h->prof_ev[i + 1]));
+  return h->prof_n;
+}
+
+const char* wsu_profile_name(wsu_handle h, int i) {
+  if (!h || i < 0 || i >= h->prof_n) return "";
+  return h->prof_names[i].c_str();
 }
 
 int wsu_debug_layer(wsu_handle h, const char* name, float* dst_dev, size_t cap, int with_halo, int64_t* dims_out,

@@ -80,8 +80,9 @@ def test_unet_uint8_input_equals_float_input(cuda_dev):
     m = _model(2, 11, cuda_dev)
     img = torch.randint(0, 256, (2, 1, 64, 64), dtype=torch.uint8, device=cuda_dev)
     y8 = m(img)
-    yf = m(img.float() / 255.)
-    assert torch.equal(y8, yf)  # x/255 is the same IEEE division on both paths (src/unet/evaluate.py:45)
+    # numpy true division like the reference (src/unet/evaluate.py:45); torch CUDA would multiply by a reciprocal
+    xf = torch.from_numpy(img.cpu().numpy().astype(np.float32) / np.float32(255.)).to(cuda_dev)
+    assert torch.equal(y8, m(xf))
 
 
 def test_unet_shape_errors(cuda_dev):

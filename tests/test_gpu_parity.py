@@ -179,7 +179,7 @@ def test_attack_signature_and_external_estimator(cuda_dev, ws_golden):
 def test_filter_float_input_and_edge_sizes(cuda_dev):
     import ws_unet_b200 as W
     rng = np.random.default_rng(0)
-    for h, w in [(3, 3), (3, 17), (9, 4), (35, 515), (130, 1031)]:
+    for h, w in [(3, 3), (3, 17), (9, 4), (3, 8), (35, 515), (35, 516), (64, 128), (130, 1031), (93, 1032)]:
         img = rng.integers(0, 256, (2, 1, h, w), dtype=np.uint8)
         d = torch.from_numpy(img).to(cuda_dev)
         for name in ['KB', 'AVG']:

@@ -1,0 +1,62 @@
+"""Per-layer device times of the UNet chain (CUDA events around every launch), halo kernel vs per-tap kernel.
+Usage (on a B200): python tools/layer_profile.py [images] [reps]"""
+import ctypes
+import sys
+
+import torch
+
+sys.path.insert(0, '.')
+import ws_unet_b200 as W
+from ws_unet_b200 import _native
+
+GF = {'e11': 0.302, 'e12': 19.327, 'e21': 9.664, 'e22': 19.327, 'e31': 9.664, 'e32': 19.327, 'upconv3': 4.295,
+      'd31': 38.655, 'd32': 19.327, 'upconv4': 4.295, 'd41': 38.655, 'd42': 19.361}
+
+
+def profile(model, imgs, lib, h, reps):
+    n = imgs.shape[0]
+    lib.wsu_set_option(h, b'profile', 1)
+    acc = None
+    for _ in range(reps):
+        W.ws_estimate(imgs, model, weighted=0, clip=True, crop=1)
+        torch.cuda.synchronize()
+        buf = (ctypes.c_float * 64)()
+        k = lib.wsu_profile_read(h, buf, 64)
+        cur = [buf[i] for i in range(k)]
+        acc = cur if acc is None else [min(a, c) for a, c in zip(acc, cur)]
+    names = [lib.wsu_profile_name(h, i).decode() for i in range(len(acc))]
+    lib.wsu_set_option(h, b'profile', 0)
+    return names, acc
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    dev = torch.device('cuda', 0)
+    torch.manual_seed(0)
+    model = W.get_model('unet_2', 1).to(dev)
+    imgs = torch.randint(0, 256, (n, 1, 512, 512), dtype=torch.uint8, device=dev)
+    lib = _native.load()
+    h = model.native_handle(dev)
+    model.set_micro_batch(n, dev)
+    res = {}
+    for halo in (1, 0):
+        lib.wsu_set_option(h, b'halo', halo)
+        beta = W.ws_estimate(imgs, model)
+        res[halo] = (profile(model, imgs, lib, h, reps), beta)
+    print('beta halo==per-tap bit-equal:', torch.equal(res[1][1], res[0][1]), ' max|d| =', (res[1][1] - res[0][1]).abs().max().item())
+    names = res[1][0][0]
+    print(f'{"layer":8s} {"halo ms":>9s} {"TF/s alg":>9s} {"issued":>8s} | {"tap ms":>9s} {"TF/s alg":>9s} {"issued":>8s}   ({n} images)')
+    tot = [0.0, 0.0]
+    for i, name in enumerate(names):
+        a, b = res[1][0][1][i], res[0][0][1][i]
+        ta, tb = GF[name] * n / a, GF[name] * n / b  # GFLOP / ms = TFLOP/s
+        tot[0] += a
+        tot[1] += b
+        print(f'{name:8s} {a:9.3f} {ta:9.1f} {3 * ta:8.1f} | {b:9.3f} {tb:9.1f} {3 * tb:8.1f}')
+    for k, t in zip(('halo', 'per-tap'), tot):
+        print(f'{k}: {t:.3f} ms / {n} images = {t / n:.4f} ms/img -> {n / t * 1e3:.1f} img/s, {202.199 * n / t:.1f} TFLOP/s algorithmic')
+
+
+if __name__ == '__main__':
+    main()

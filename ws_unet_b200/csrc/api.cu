@@ -137,6 +137,7 @@ struct wsu_context {
   std::vector<std::string> prof_names;
   int prof_n = 0;
   int last_nimg = 0;  // images in the last micro-batch that ran
+  bool use_halo = true;  // 3x3 layers through conv_halo_kernel (option "halo"; 0 = per-tap reload kernel, for A/B runs)
 };
 
 namespace {
@@ -195,6 +196,10 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   if (rc) return rc;
   rc = make_act_tmap(&p.tmapA1, src1 ? *src1 : src0, TW, TH);
   if (rc) return rc;
+  rc = make_act_tmap(&p.tmapH0, src0, kHaloTW + 2, kHaloTH + 2);
+  if (rc) return rc;
+  rc = make_act_tmap(&p.tmapH1, src1 ? *src1 : src0, kHaloTW + 2, kHaloTH + 2);
+  if (rc) return rc;
   p.wpack = lw.wpack;
   p.bias = lw.bias;
   p.cblocks0 = src0.C / 64;
@@ -212,6 +217,10 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   p.tiles_x = (p.W + TW * m_sub - 1) / (TW * m_sub);
   p.tiles_y = (p.H + TH - 1) / TH;
   p.total_tiles = p.B * p.tiles_y * p.tiles_x * p.n_tiles * p.npos;
+  p.sub_x = (p.W + kHaloTW - 1) / kHaloTW;
+  p.sub_y = (p.H + kHaloTH - 1) / kHaloTH;
+  p.total_sub = p.B * p.sub_x * p.sub_y;
+  p.total_items = ((p.total_sub + halo_msub(lw.n_tile) - 1) / halo_msub(lw.n_tile)) * p.n_tiles;
   p.relu = relu;
   p.upsample = upsample;
   if (out) p.out = *out;
@@ -219,7 +228,7 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   if (epi == EPI_HEAD) {
     std::memcpy(p.wout, h->wout, sizeof(p.wout));
     p.bout = h->bout;
-    pl.tiles_per_img = p.tiles_x * p.tiles_y;
+    pl.tiles_per_img = std::max(p.tiles_x * p.tiles_y, p.sub_x * p.sub_y);  // partial records: v1 tiles or halo boxes
   }
   pl.convs.push_back({p, {lw.n_tile, epi}});
   pl.conv_names.push_back(lname);
@@ -341,9 +350,12 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
   for (size_t i = 0; i < pl.convs.size(); ++i) {
     ConvParams p = pl.convs[i].first;
     const int n_tile = pl.convs[i].second.first, epi = pl.convs[i].second.second;
+    const bool halo = h->use_halo && p.ntaps == 9;
     if (nimg != pl.mb) {
       p.B = nimg;
       p.total_tiles = nimg * p.tiles_y * p.tiles_x * p.n_tiles * p.npos;
+      p.total_sub = nimg * p.sub_x * p.sub_y;
+      p.total_items = ((p.total_sub + halo_msub(n_tile) - 1) / halo_msub(n_tile)) * p.n_tiles;
     }
     if (epi == EPI_HEAD) {
       p.img = ws_img;
@@ -354,7 +366,10 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
       p.crop = crop;
     }
     mark(i + 1);
-    LAUNCH_TRY(launch_conv_mma(p, n_tile, epi, h->num_sms, st));
+    if (halo)
+      LAUNCH_TRY(launch_conv_halo(p, n_tile, epi, h->num_sms, st));
+    else
+      LAUNCH_TRY(launch_conv_mma(p, n_tile, epi, h->num_sms, st));
   }
   mark(pl.convs.size() + 1);
   return WSU_OK;
@@ -387,7 +402,9 @@ int unet_ws_device(wsu_context* h, const void* img, int dtype, int B, int H, int
       return rc;
     if (want_ws) {
       const float npix = crop ? float(H - 2) * float(W - 2) : float(H) * float(W);
-      LAUNCH_TRY(launch_finalize(h->plan->partials, h->plan->tiles_per_img * 4, nimg, npix, clip, 0, beta + b0,
+      const ConvParams& hp = h->plan->convs.back().first;
+      const int records = h->use_halo ? hp.sub_x * hp.sub_y * 4 : hp.tiles_x * hp.tiles_y * 8;  // one per epilogue warp
+      LAUNCH_TRY(launch_finalize(h->plan->partials, records, nimg, npix, clip, 0, beta + b0,
                                  l1 ? l1 + b0 : nullptr, st));
     }
   }
@@ -467,6 +484,10 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
   if (!std::strcmp(key, "micro_batch")) {
     if (value < 0) return fail(WSU_ERR_INVALID, "micro_batch must be >= 0");
     h->micro_batch = value;
+    return WSU_OK;
+  }
+  if (!std::strcmp(key, "halo")) {
+    h->use_halo = value != 0;
     return WSU_OK;
   }
   if (!std::strcmp(key, "profile")) {
@@ -674,10 +695,15 @@ int wsu_filter_ws_estimate(int device, const void* img_dev, int img_dtype, int k
   CUDA_TRY(cudaSetDevice(device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partials = nullptr;
-  const int strips = filter_ws_strips(H);
-  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partials), size_t(B) * strips * kPartialSlots * 4, st));
-  LAUNCH_TRY(launch_filter_ws(img_dev, img_dtype == WSU_F32, B, H, W, kind, weighted, correct_bias, nullptr, partials, st));
-  LAUNCH_TRY(launch_finalize(partials, strips, B, float(H - 2) * float(W - 2), clip, correct_bias, beta_dev, l1_dev, st));
+  int records = filter_ws_strips(H);
+  const bool fast = filter_ws_fast_ok(img_dev, img_dtype == WSU_F32, W, kind, correct_bias, nullptr);
+  if (fast) records = filter_ws_fast_records(H, W);
+  CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partials), size_t(B) * records * kPartialSlots * 4, st));
+  if (fast)
+    LAUNCH_TRY(launch_filter_ws_fast(img_dev, B, H, W, kind, weighted, partials, st));
+  else
+    LAUNCH_TRY(launch_filter_ws(img_dev, img_dtype == WSU_F32, B, H, W, kind, weighted, correct_bias, nullptr, partials, st));
+  LAUNCH_TRY(launch_finalize(partials, records, B, float(H - 2) * float(W - 2), clip, correct_bias, beta_dev, l1_dev, st));
   CUDA_TRY(cudaFreeAsync(partials, st));
   return WSU_OK;
 }

@@ -21,7 +21,7 @@ namespace wsu {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;          // warps: 0 TMA, 1 MMA, 2..9 epilogue (two groups of four lane quadrants)
 constexpr int kABytes = 2 * 128 * 128;  // hi + lo tile of 128 pixels x 64 channels
 constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
 
@@ -74,6 +74,118 @@ __device__ __forceinline__ void store_pixel32(const Act& o, int b, int oy, int o
   }
 }
 
+// Epilogue of one 128-pixel box: thread owns pixel (y, x) = TMEM lane; tbase addresses its accumulator columns.
+// pool_xor: lane distance of the vertical 2x2-pool partner (= box width in pixels).
+// STACKED (Cout = 64 layers of the halo kernel): the accumulator is 128 columns wide, columns [0,64) hold
+// (Ahi + Alo) * Whi and columns [64,128) hold Ahi * Wlo of the same 64 output channels; they are summed here.
+template <int N_TILE, int EPI, bool STACKED>
+__device__ __forceinline__ void load_acc32(uint32_t taddr, float (&f)[32]) {
+  uint32_t v[32];
+  tmem_ld32(taddr, v);
+  if constexpr (STACKED) {
+    uint32_t w[32];
+    tmem_ld32(taddr + 64, w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + __uint_as_float(w[i]);
+  } else {
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+  }
+}
+
+template <int N_TILE, int EPI, bool STACKED = false>
+__device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* sBias, uint32_t tbase, int b, int y, int x,
+                                             bool valid, int nt, int pos, int tx, int ty, int pool_xor, WsAcc& acc) {
+        if constexpr (EPI == EPI_ACT) {
+#pragma unroll 1
+          for (int cc = 0; cc < N_TILE / 32; ++cc) {
+            const int n0 = nt * N_TILE + cc * 32;
+            float f[32];
+            load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              f[i] += sBias[n0 + i];
+              if (p.relu) f[i] = fmaxf(f[i], 0.f);
+            }
+            uint32_t h[16], l[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
+            if (valid) {
+              const int oy = p.upsample ? 2 * y + (pos >> 1) : y;
+              const int ox = p.upsample ? 2 * x + (pos & 1) : x;
+              store_pixel32(p.out, b, oy, ox, n0, h, l);
+            }
+            if (p.do_pool) {
+              // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
+                f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], pool_xor));
+              }
+              if (valid && !(tx & 1) && !(ty & 1)) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
+                store_pixel32(p.pool, b, y >> 1, x >> 1, n0, h, l);
+              }
+            }
+          }
+        } else {
+          // 1x1 outconv over the 64 ReLU'd channels of d42, sigmoid, WS residual terms
+          float z = p.bout;
+#pragma unroll 1
+          for (int cc = 0; cc < N_TILE / 32; ++cc) {
+            float f[32];
+            load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float a = fmaxf(f[i] + sBias[cc * 32 + i], 0.f);
+              z = fmaf(a, p.wout[cc * 32 + i], z);
+            }
+          }
+          if (valid) {
+            const float s = 1.f / (1.f + expf(-z));
+            const size_t pix = (size_t(b) * p.H + y) * p.W + x;
+            if (p.yhat) p.yhat[pix] = s;
+            const bool inside = p.crop ? (y >= 1 && y < p.H - 1 && x >= 1 && x < p.W - 1) : true;
+            if (p.img && inside) {
+              const float xhat = s * 255.f;
+              float xv, xbar, s1 = 0.f, s2 = 0.f;
+              if (p.img_is_float) {
+                const float* im = static_cast<const float*>(p.img);
+                ws_load_f32(im[pix], xv, xbar);
+                if (p.weighted != WS_UNWEIGHTED) {
+                  for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                      if (dy == 0 && dx == 0) continue;
+                      const float q = im[pix + dy * p.W + dx] * 255.f;
+                      s1 += q;
+                      s2 = fmaf(q, q, s2);
+                    }
+                }
+              } else {
+                const uint8_t* im = static_cast<const uint8_t*>(p.img);
+                ws_load_u8(im[pix], xv, xbar);
+                if (p.weighted != WS_UNWEIGHTED) {
+                  int i1 = 0, i2 = 0;
+                  for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx) {
+                      if (dy == 0 && dx == 0) continue;
+                      const int q = im[pix + dy * p.W + dx];
+                      i1 += q;
+                      i2 += q * q;
+                    }
+                  s1 = float(i1);
+                  s2 = float(i2);
+                }
+              }
+              ws_accumulate(acc, xv, xbar, xhat, ws_weight(p.weighted, s1, s2));
+            }
+          }
+        }
+      }
+
 template <int N_TILE, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_constant__ ConvParams p) {
   using C = Cfg<N_TILE>;
@@ -102,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_cons
     prefetch_tmap(&p.tmapA1);
     for (int i = 0; i < C::SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::SW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -114,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_cons
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int as = 0, ws = 0;
       uint32_t aph = 0, wph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -143,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (single thread)
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(N_TILE);
       int as = 0, ws = 0, acs = 0;
       uint32_t aph = 0, wph = 0, acph = 0;
@@ -184,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_cons
   } else {
     // ===================================================== epilogue warps (TMEM -> registers -> HBM)
     const int quad = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int grp = (warp - 2) >> 2;            // epilogue group: boxes j = grp, grp + 2, ...
     const int row = quad * 32 + lane;           // pixel row of the 128-pixel box
     const int ty = row / p.TW, tx = row - ty * p.TW;
     int acs = 0;
@@ -195,99 +308,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_cons
       const int y = t.y0 + ty;
       WsAcc acc;
 #pragma unroll 1
-      for (int j = 0; j < M_SUB; ++j) {
+      for (int j = grp; j < M_SUB; j += 2) {
         const int x = t.x0 + j * p.TW + tx;
         const bool valid = (y < p.H) && (x < p.W);
         const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acs * kAccCols + j * N_TILE);
-        if constexpr (EPI == EPI_ACT) {
-#pragma unroll 1
-          for (int cc = 0; cc < N_TILE / 32; ++cc) {
-            uint32_t v[32];
-            tmem_ld32(tbase + cc * 32, v);
-            tmem_ld_wait();
-            const int n0 = t.nt * N_TILE + cc * 32;
-            float f[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              f[i] = __uint_as_float(v[i]) + sBias[n0 + i];
-              if (p.relu) f[i] = fmaxf(f[i], 0.f);
-            }
-            uint32_t h[16], l[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
-            if (valid) {
-              const int oy = p.upsample ? 2 * y + (t.pos >> 1) : y;
-              const int ox = p.upsample ? 2 * x + (t.pos & 1) : x;
-              store_pixel32(p.out, t.b, oy, ox, n0, h, l);
-            }
-            if (p.do_pool) {
-              // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16)
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
-                f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 16));
-              }
-              if (valid && !(tx & 1) && !(ty & 1)) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
-                store_pixel32(p.pool, t.b, y >> 1, x >> 1, n0, h, l);
-              }
-            }
-          }
-        } else {
-          // 1x1 outconv over the 64 ReLU'd channels of d42, sigmoid, WS residual terms
-          float z = p.bout;
-#pragma unroll 1
-          for (int cc = 0; cc < N_TILE / 32; ++cc) {
-            uint32_t v[32];
-            tmem_ld32(tbase + cc * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float a = fmaxf(__uint_as_float(v[i]) + sBias[cc * 32 + i], 0.f);
-              z = fmaf(a, p.wout[cc * 32 + i], z);
-            }
-          }
-          if (valid) {
-            const float s = 1.f / (1.f + expf(-z));
-            const size_t pix = (size_t(t.b) * p.H + y) * p.W + x;
-            if (p.yhat) p.yhat[pix] = s;
-            const bool inside = p.crop ? (y >= 1 && y < p.H - 1 && x >= 1 && x < p.W - 1) : true;
-            if (p.img && inside) {
-              const float xhat = s * 255.f;
-              float xv, xbar, s1 = 0.f, s2 = 0.f;
-              if (p.img_is_float) {
-                const float* im = static_cast<const float*>(p.img);
-                ws_load_f32(im[pix], xv, xbar);
-                if (p.weighted != WS_UNWEIGHTED) {
-                  for (int dy = -1; dy <= 1; ++dy)
-                    for (int dx = -1; dx <= 1; ++dx) {
-                      if (dy == 0 && dx == 0) continue;
-                      const float q = im[pix + dy * p.W + dx] * 255.f;
-                      s1 += q;
-                      s2 = fmaf(q, q, s2);
-                    }
-                }
-              } else {
-                const uint8_t* im = static_cast<const uint8_t*>(p.img);
-                ws_load_u8(im[pix], xv, xbar);
-                if (p.weighted != WS_UNWEIGHTED) {
-                  int i1 = 0, i2 = 0;
-                  for (int dy = -1; dy <= 1; ++dy)
-                    for (int dx = -1; dx <= 1; ++dx) {
-                      if (dy == 0 && dx == 0) continue;
-                      const int q = im[pix + dy * p.W + dx];
-                      i1 += q;
-                      i2 += q * q;
-                    }
-                  s1 = float(i1);
-                  s2 = float(i2);
-                }
-              }
-              ws_accumulate(acc, xv, xbar, xhat, ws_weight(p.weighted, s1, s2));
-            }
-          }
-        }
+        epilogue_box<N_TILE, EPI>(p, sBias, tbase, t.b, y, x, valid, t.nt, t.pos, tx, ty, p.TW, acc);
       }
       // all TMEM reads of this stage are complete -> hand the accumulators back to the MMA warp
       tc_fence_before();
@@ -297,9 +322,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_cons
       if constexpr (EPI == EPI_HEAD) {
         if (p.partials) {
           const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1);
-          if (lane == 0) {
+          if (elect_one()) {
             const size_t tiles_per_img = size_t(p.tiles_x) * p.tiles_y;
-            float* dst = p.partials + ((size_t(t.b) * tiles_per_img + t.tile_in_img) * 4 + quad) * kPartialSlots;
+            float* dst = p.partials + ((size_t(t.b) * tiles_per_img + t.tile_in_img) * 8 + (warp - 2)) * kPartialSlots;
             dst[0] = wr;
             dst[1] = w;
             dst[2] = l1;
@@ -325,6 +350,251 @@ cudaError_t launch_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+
+// ================================================================================================ halo kernel
+// 3x3 convolution with ONE activation load per (box, 64-channel block): the TMA box is the 8x16-pixel output box plus
+// its 1-pixel halo (10 x 18 pixels x 64 channels x {hi, lo}); tap (dy, dx) is the same shared-memory tile read through
+// a descriptor whose start is shifted by (dy*10 + dx) rows and whose 8-row atoms are 10 rows (1280 B) apart.
+// L2 -> SM activation traffic drops from 9 x 32 KB to 45 KB per box and channel block.
+// Warp roles: 0 = activation (TMA box) producer, 1 = MMA issuer, 2..5 = epilogue, 6 = weight producer.
+constexpr int kHaloThreads = 352;  // warps: 0 box producer, 1 MMA, 2..9 epilogue (group g owns box g), 10 weight producer
+constexpr int kHaloRows = (kHaloTW + 2) * (kHaloTH + 2);  // 180 rows of 128 B per plane
+constexpr int kHaloABytes = 2 * kHaloRows * 128;           // 46080
+constexpr uint32_t kHaloSBO = (kHaloTW + 2) * 128;         // 1280
+
+// Operand-bandwidth note: an M=128 x N x K=16 MMA takes N/2 tensor cycles but reads 4 KB (A) + N*32 B (B) from shared
+// memory at 128 B/cycle. For Cout = 64 three N=64 MMAs (hi*hi, lo*hi, hi*lo) need 18 KB = 144 smem cycles for 96 tensor
+// cycles. Stacking [Whi; Wlo] as ONE 128-row B tile turns hi*hi and hi*lo into a single N=128 MMA (A read once):
+// 14 KB = 112 smem cycles per 96 tensor cycles. The accumulator is then 128 columns wide and the epilogue adds halves.
+template <int N_TILE>
+struct HCfg {
+  static constexpr bool STACKED = (N_TILE == 64);
+  static constexpr int M_SUB = halo_msub(N_TILE);
+  static constexpr int ACC_W = 128;                          // TMEM columns per box (stacked 2 x 64, or 128)
+  static constexpr int SA = 3;                               // M_SUB resident boxes + 1 prefetch slot
+  static constexpr int W_BYTES = STACKED ? 2 * N_TILE * 128  // ring slot: whole (hi, lo) chunk, contiguous
+                                         : N_TILE * 128;     //            or one plane of one tap
+  static constexpr int W_PER_TAP = STACKED ? 1 : 2;          // ring slots consumed per tap
+  static constexpr int SW = STACKED ? 4 : 5;
+  static constexpr int BIAS_BYTES = (N_TILE == 64) ? 256 : 4096;
+  static constexpr int SMEM = SA * kHaloABytes + SW * W_BYTES + 1024 + BIAS_BYTES + 256;
+};
+
+struct BoxCoord {
+  int b, y0, x0, sub_in_img;
+};
+__device__ __forceinline__ BoxCoord decode_box(const ConvParams& p, int s) {
+  BoxCoord c;
+  const int tx = s % p.sub_x;
+  const int r = s / p.sub_x;
+  const int ty = r % p.sub_y;
+  c.b = r / p.sub_y;
+  c.x0 = tx * kHaloTW;
+  c.y0 = ty * kHaloTH;
+  c.sub_in_img = ty * p.sub_x + tx;
+  return c;
+}
+
+template <int N_TILE, int EPI>
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+  using C = HCfg<N_TILE>;
+  constexpr int M_SUB = C::M_SUB;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + C::SA * kHaloABytes;
+  float* sBias = reinterpret_cast<float*>(sW + C::SW * C::W_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + C::BIAS_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + C::SA;
+  uint64_t* w_full = a_empty + C::SA;
+  uint64_t* w_empty = w_full + C::SW;
+  uint64_t* acc_full = w_empty + C::SW;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmapH0);
+    prefetch_tmap(&p.tmapH1);
+    for (int i = 0; i < C::SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::SW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < p.cout && i < C::BIAS_BYTES / 4; i += kHaloThreads) sBias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== activation producer: one haloed box per (box, channel block)
+    if (elect_one()) {
+      int as = 0;
+      uint32_t aph = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int s0 = (item / p.n_tiles) * M_SUB;
+        const int nsub = min(M_SUB, p.total_sub - s0);
+        for (int c = 0; c < p.cblocks; ++c) {
+          const bool src0 = c < p.cblocks0;
+          const CUtensorMap* tm = src0 ? &p.tmapH0 : &p.tmapH1;
+          const int ch = (src0 ? c : c - p.cblocks0) * 64;
+          for (int j = 0; j < nsub; ++j) {
+            const BoxCoord bc = decode_box(p, s0 + j);
+            mbar_wait(&a_empty[as], aph ^ 1);
+            mbar_arrive_expect_tx(&a_full[as], kHaloABytes);
+            // padded coords of pixel (y, x) are (y+1, x+1): the box with its halo starts at (y0, x0)
+            tma_load_5d(sA + as * kHaloABytes, tm, &a_full[as], ch, bc.x0, bc.y0, bc.b, 0);
+            if (++as == C::SA) { as = 0; aph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================================================== weight producer: ring slots of every (block, tap)
+    if (elect_one()) {
+      int ws = 0;
+      uint32_t wph = 0;
+      const int halves = p.cblocks * 9 * C::W_PER_TAP;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int nt = item % p.n_tiles;
+        const uint8_t* wsrc = p.wpack + size_t(nt) * halves * C::W_BYTES;
+        for (int hh = 0; hh < halves; ++hh) {
+          mbar_wait(&w_empty[ws], wph ^ 1);
+          mbar_arrive_expect_tx(&w_full[ws], C::W_BYTES);
+          bulk_load(sW + ws * C::W_BYTES, wsrc + size_t(hh) * C::W_BYTES, C::W_BYTES, &w_full[ws]);
+          if (++ws == C::SW) { ws = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(N_TILE);
+      int as = 0, ws = 0, acs = 0;
+      uint32_t aph = 0, wph = 0, acph = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int s0 = (item / p.n_tiles) * M_SUB;
+        const int nsub = min(M_SUB, p.total_sub - s0);
+        mbar_wait(&acc_empty[acs], acph ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < p.cblocks; ++c) {
+          uint32_t a_slot[M_SUB];
+          for (int tap = 0; tap < 9; ++tap) {
+            const int ws_hi = ws;
+            mbar_wait(&w_full[ws], wph);
+            if (++ws == C::SW) { ws = 0; wph ^= 1; }
+            int ws_lo = ws_hi;
+            if constexpr (!C::STACKED) {
+              ws_lo = ws;
+              mbar_wait(&w_full[ws], wph);
+              if (++ws == C::SW) { ws = 0; wph ^= 1; }
+            }
+            const uint32_t w_hi = smem_u32(sW + ws_hi * C::W_BYTES);
+            const uint32_t w_lo = C::STACKED ? w_hi + N_TILE * 128 : smem_u32(sW + ws_lo * C::W_BYTES);
+            const uint32_t tap_off = uint32_t((tap / 3) * (kHaloTW + 2) + (tap % 3)) * 128;
+#pragma unroll
+            for (int j = 0; j < M_SUB; ++j) {
+              if (j < nsub) {
+                if (tap == 0) {
+                  mbar_wait(&a_full[as], aph);
+                  a_slot[j] = uint32_t(as);
+                  if (++as == C::SA) { as = 0; aph ^= 1; }
+                }
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(sA + a_slot[j] * kHaloABytes) + tap_off;
+                const uint32_t a_lo = a_hi + kHaloRows * 128;
+                const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t da_hi = make_sw128_desc(a_hi + k * 32, kHaloSBO);
+                  const uint64_t da_lo = make_sw128_desc(a_lo + k * 32, kHaloSBO);
+                  const uint64_t dw_hi = make_sw128_desc(w_hi + k * 32);
+                  if constexpr (C::STACKED) {
+                    // B tile of 128 rows = [Whi; Wlo]: columns [0,64) += Ahi*Whi, [64,128) += Ahi*Wlo
+                    umma_bf16(d, da_hi, dw_hi, make_idesc_bf16(128), (c | tap | k) != 0);
+                    umma_bf16(d, da_lo, dw_hi, make_idesc_bf16(64), 1);   // columns [0,64) += Alo*Whi
+                  } else {
+                    const uint64_t dw_lo = make_sw128_desc(w_lo + k * 32);
+                    umma_bf16(d, da_hi, dw_hi, idesc, (c | tap | k) != 0);
+                    umma_bf16(d, da_lo, dw_hi, idesc, 1);
+                    umma_bf16(d, da_hi, dw_lo, idesc, 1);
+                  }
+                }
+                if (tap == 8) umma_commit(&a_empty[a_slot[j]]);
+              }
+            }
+            umma_commit(&w_empty[ws_hi]);
+            if constexpr (!C::STACKED) umma_commit(&w_empty[ws_lo]);
+          }
+        }
+        umma_commit(&acc_full[acs]);
+        if (++acs == 2) { acs = 0; acph ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps
+    const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;  // group g finishes box g of every work item
+    const int row = quad * 32 + lane;
+    const int ty = row / kHaloTW, tx = row % kHaloTW;
+    int acs = 0;
+    uint32_t acph = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int nt = item % p.n_tiles;
+      const int s0 = (item / p.n_tiles) * M_SUB;
+      const int nsub = min(M_SUB, p.total_sub - s0);
+      mbar_wait(&acc_full[acs], acph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = grp; j < nsub; j += 2) {
+        const BoxCoord bc = decode_box(p, s0 + j);
+        const int y = bc.y0 + ty, x = bc.x0 + tx;
+        const bool valid = (y < p.H) && (x < p.W);
+        const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acs * kAccCols + j * C::ACC_W);
+        WsAcc acc;
+        epilogue_box<N_TILE, EPI, C::STACKED>(p, sBias, tbase, bc.b, y, x, valid, nt, 0, tx, ty, kHaloTW, acc);
+        if constexpr (EPI == EPI_HEAD) {
+          if (p.partials) {
+            const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1);
+            if (elect_one()) {
+              const size_t subs_per_img = size_t(p.sub_x) * p.sub_y;
+              float* dst = p.partials + ((size_t(bc.b) * subs_per_img + bc.sub_in_img) * 4 + quad) * kPartialSlots;
+              dst[0] = wr;
+              dst[1] = w;
+              dst[2] = l1;
+              dst[3] = 0.f;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acs]);
+      if (++acs == 2) { acs = 0; acph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int N_TILE, int EPI>
+cudaError_t launch_halo_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  const int grid = p.total_items < num_sms ? p.total_items : num_sms;
+  conv_halo_kernel<N_TILE, EPI><<<grid, kHaloThreads, HCfg<N_TILE>::SMEM, stream>>>(p);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t conv_mma_init() {
@@ -334,6 +604,12 @@ cudaError_t conv_mma_init() {
   e = cudaFuncSetAttribute(conv_mma_kernel<128, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_mma_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo_kernel<64, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<64>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo_kernel<128, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<128>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<64>::SMEM);
   return e;
 }
 
@@ -349,4 +625,17 @@ cudaError_t launch_conv_mma(const ConvParams& p, int n_tile, int epi, int num_sm
   return cudaErrorInvalidValue;
 }
 
+}  // namespace wsu
+
+namespace wsu {
+cudaError_t launch_conv_halo(const ConvParams& p, int n_tile, int epi, int num_sms, cudaStream_t stream) {
+  if (p.ntaps != 9 || p.npos != 1 || p.upsample) return cudaErrorInvalidValue;
+  if (epi == EPI_HEAD) {
+    if (n_tile != 64 || p.n_tiles != 1) return cudaErrorInvalidValue;
+    return launch_halo_t<64, EPI_HEAD>(p, num_sms, stream);
+  }
+  if (n_tile == 64) return p.n_tiles == 1 ? launch_halo_t<64, EPI_ACT>(p, num_sms, stream) : cudaErrorInvalidValue;
+  if (n_tile == 128) return launch_halo_t<128, EPI_ACT>(p, num_sms, stream);
+  return cudaErrorInvalidValue;
+}
 }  // namespace wsu

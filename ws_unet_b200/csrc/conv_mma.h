@@ -13,6 +13,8 @@ enum : int { EPI_ACT = 0, EPI_HEAD = 1 };
 struct alignas(64) ConvParams {
   CUtensorMap tmapA0;  // first concat source  (upsampled path, unet.py:178 puts it first)
   CUtensorMap tmapA1;  // second concat source (skip); unused when cblocks == cblocks0
+  CUtensorMap tmapH0;  // same sources with the haloed box (64 ch, 10, 18, 1 img, 2 planes) of the halo kernel
+  CUtensorMap tmapH1;
   const uint8_t* wpack;  // packed + pre-swizzled split-bf16 weights, see pack_conv_weights()
   const float* bias;     // [Cout]
   int cblocks0;          // 64-channel blocks taken from source 0
@@ -26,6 +28,10 @@ struct alignas(64) ConvParams {
   int TW, TH;            // sub-tile box (TW*TH == 128 pixels)
   int tiles_x, tiles_y;  // super-tiles (M_SUB sub-tiles side by side in x) per image
   int total_tiles;
+  // halo kernel: 8x16-pixel boxes enumerated row-major over (image, box row, box column)
+  int sub_x, sub_y;      // boxes per image row / column
+  int total_sub;         // B * sub_y * sub_x
+  int total_items;       // ceil(total_sub / M_SUB) * n_tiles
   // EPI_ACT
   int relu;
   int upsample;          // 1: write phase (pos>>1, pos&1) of a 2x upsampled map (ConvTranspose2d k=2,s=2)
@@ -47,6 +53,10 @@ struct alignas(64) ConvParams {
 constexpr int wchunk_bytes(int n_tile) { return n_tile * 64 * 2 * 2; }
 
 cudaError_t launch_conv_mma(const ConvParams& p, int n_tile, int epi, int num_sms, cudaStream_t stream);
+// 3x3 convolutions only: one haloed TMA box per (box, channel block) feeds all 9 taps
+cudaError_t launch_conv_halo(const ConvParams& p, int n_tile, int epi, int num_sms, cudaStream_t stream);
+constexpr int halo_msub(int) { return 2; }
+constexpr int kHaloTW = 8, kHaloTH = 16;
 cudaError_t conv_mma_init();  // sets max dynamic shared memory on every instantiation
 
 }  // namespace wsu

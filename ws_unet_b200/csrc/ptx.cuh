@@ -116,11 +116,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // K-major, 128-byte-swizzled operand tile: rows of 128 B (64 bf16), 8-row atoms 1024 B apart.
 // Field layout per the sm_100 shared-memory matrix descriptor (start>>4, LBO, SBO, version=1, SW128=2).
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+// The 128-byte swizzle is applied to ABSOLUTE shared-memory address bits (measured, profiles/r01_umma_descriptor_probe.log):
+// a start address offset by any number of 128-byte rows and an atom stride (sbo) that is not a multiple of 1024 both
+// read what TMA wrote, so one haloed box serves all 9 taps of a 3x3 convolution.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
   d |= uint64_t(1) << 16;                        // leading byte offset (unused for swizzled K-major) = 1
-  d |= uint64_t(1024 >> 4) << 32;                // stride byte offset between 8-row atoms
+  d |= uint64_t(sbo_bytes >> 4) << 32;           // stride byte offset between 8-row atoms
   d |= uint64_t(1) << 46;                        // descriptor version (Blackwell)
   d |= uint64_t(2) << 61;                        // SWIZZLE_128B
   return d;

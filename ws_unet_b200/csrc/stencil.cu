@@ -17,10 +17,87 @@ namespace wsu {
 namespace {
 
 // ------------------------------------------------------------------------------------------------ e11
-// 8 threads per pixel, 8 output channels each: a warp writes 4 adjacent pixels = 512 contiguous bytes per plane.
+// One CTA = one 128-pixel row segment of one image. The 3 input rows (reflect-resolved, already scaled to [0,1]) are
+// staged in shared memory; thread (pixel lane pl = tid/8, channel group cg = tid%8) keeps its 8 x (9*cin) weights in
+// registers and walks 4 pixels. 8 threads write one pixel's 64 channels = 128 contiguous bytes per plane, a warp
+// writes 4 adjacent pixels = 512 contiguous bytes.
+constexpr int kE11Seg = 128;   // pixels per row segment
+constexpr int kE11Rows = 8;    // rows per CTA (weights are loaded into registers once per CTA)
+
+template <bool kFloatIn, int CIN>
+__global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict__ img, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, Act out, int segs_per_row,
+                                                         int row_groups) {
+  __shared__ float rows[CIN][kE11Rows + 2][kE11Seg + 2];
+  const int H = out.H, W = out.W;
+  const int seg = blockIdx.x % segs_per_row;
+  const int y0 = ((blockIdx.x / segs_per_row) % row_groups) * kE11Rows;
+  const int b = blockIdx.x / (segs_per_row * row_groups);
+  const int x0 = seg * kE11Seg;
+  for (int i = threadIdx.x; i < CIN * (kE11Rows + 2) * (kE11Seg + 2); i += 256) {
+    const int col = i % (kE11Seg + 2);
+    const int r = (i / (kE11Seg + 2)) % (kE11Rows + 2);
+    const int ci = i / ((kE11Rows + 2) * (kE11Seg + 2));
+    int yy = y0 + r - 1;
+    yy = min(yy, 2 * H - 2);                                // rows past a ragged last group: keep the index valid
+    yy = yy < 0 ? -yy : (yy >= H ? 2 * H - 2 - yy : yy);  // reflect (unet.py:73)
+    int xx = x0 + col - 1;
+    xx = xx < 0 ? -xx : (xx >= W ? 2 * W - 2 - xx : xx);
+    xx = min(max(xx, 0), W - 1);                            // columns past a ragged last segment: any valid pixel
+    const size_t o = ((size_t(b) * CIN + ci) * H + yy) * W + xx;
+    float v;
+    if constexpr (kFloatIn) v = static_cast<const float*>(img)[o];
+    else v = __fdiv_rn(float(static_cast<const uint8_t*>(img)[o]), 255.f);  // x / 255. of src/unet/evaluate.py:45
+    rows[ci][r][col] = v;
+  }
+  const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  float wr[8][CIN * 9], bs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bs[i] = bias[cg * 8 + i];
+#pragma unroll
+    for (int t = 0; t < CIN * 9; ++t) wr[i][t] = w[(cg * 8 + i) * CIN * 9 + t];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int it = 0; it < kE11Rows * (kE11Seg / 32); ++it) {
+    const int ry = it / (kE11Seg / 32);
+    const int y = y0 + ry;
+    const int lx = (it % (kE11Seg / 32)) * 32 + pl;
+    const int x = x0 + lx;
+    if (y >= H) break;
+    if (x >= W) continue;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = bs[i];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float v = rows[ci][ry + dy][lx + dx];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, wr[i][ci * 9 + dy * 3 + dx], acc[i]);
+        }
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_pack2(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f), h[i], l[i]);
+    int ys[3], xs[3];
+    const int ny = halo_targets(y, H, ys), nx = halo_targets(x, W, xs);
+    for (int iy = 0; iy < ny; ++iy)
+      for (int ix = 0; ix < nx; ++ix) {
+        const size_t off = ((size_t(b) * (H + 2) + ys[iy]) * (W + 2) + xs[ix]) * out.C + cg * 8;
+        *reinterpret_cast<uint4*>(out.base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(out.base + out.plane + off) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+  }
+}
+
+// generic fallback for in_channels > kE11MaxCin: 8 threads per pixel, weights in shared memory
 template <bool kFloatIn>
-__global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict__ img, int cin, const float* __restrict__ w,
-                                                         const float* __restrict__ bias, Act out) {
+__global__ void __launch_bounds__(256) first_conv_generic_kernel(const void* __restrict__ img, int cin, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, Act out) {
   extern __shared__ float sw[];  // [64][cin*9] + [64] bias
   const int kk = cin * 9;
   for (int i = threadIdx.x; i < 64 * kk; i += blockDim.x) sw[i] = w[i];
@@ -31,7 +108,7 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict_
   const size_t gid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t pix = gid >> 3;
   if (pix >= npix) return;
-  const int cg = int(gid & 7);  // channel group
+  const int cg = int(gid & 7);
   const int x = int(pix % W);
   const int y = int((pix / W) % H);
   const int b = int(pix / (size_t(W) * H));
@@ -43,17 +120,14 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict_
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
       int yy = y + dy - 1;
-      yy = yy < 0 ? -yy : (yy >= H ? 2 * H - 2 - yy : yy);  // reflect (unet.py:73)
+      yy = yy < 0 ? -yy : (yy >= H ? 2 * H - 2 - yy : yy);
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
         int xx = x + dx - 1;
         xx = xx < 0 ? -xx : (xx >= W ? 2 * W - 2 - xx : xx);
         const size_t o = ((size_t(b) * cin + ci) * H + yy) * W + xx;
-        if constexpr (kFloatIn) {
-          in[dy * 3 + dx] = static_cast<const float*>(img)[o];
-        } else {
-          in[dy * 3 + dx] = __fdiv_rn(float(static_cast<const uint8_t*>(img)[o]), 255.f);
-        }
+        if constexpr (kFloatIn) in[dy * 3 + dx] = static_cast<const float*>(img)[o];
+        else in[dy * 3 + dx] = __fdiv_rn(float(static_cast<const uint8_t*>(img)[o]), 255.f);
       }
     }
 #pragma unroll
@@ -179,6 +253,139 @@ __global__ void __launch_bounds__(kFThreads) filter_ws_kernel(const void* __rest
     float s = 0.f;
     for (int wv = 0; wv < kFThreads / 32; ++wv) s += red[wv][threadIdx.x];
     partials[(size_t(b) * strips + strip) * kPartialSlots + threadIdx.x] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fast filter WS
+// Register sliding-window version for the common case (uint8 image, KB or AVG predictor, no bias term, no x_hat
+// output, W % 4 == 0): a thread owns 4 adjacent columns and walks down kFastRows rows, keeping the 3x6 neighbourhood
+// in registers; one 32-bit load per thread and row (6 rows in flight), neighbour columns through warp shuffles.
+// The stencil is evaluated in exact integer arithmetic (4*(x - x_hat) for KB, 8*(x - x_hat) for AVG); the unweighted
+// sums stay integers until the per-CTA partial, which is emitted as two exactly representable floats.
+constexpr int kFastRows = 30;      // interior rows per CTA (5 chunks of 6)
+constexpr int kFastThreads = 128;  // x 4 pixels = 512 columns per CTA
+
+template <int KIND, int WEIGHTED>
+__global__ void __launch_bounds__(kFastThreads) filter_ws_fast_kernel(const uint8_t* __restrict__ img, int H, int W,
+                                                                      float* __restrict__ partials, int strips, int xtiles) {
+  const int xt = blockIdx.x % xtiles;
+  const int strip = (blockIdx.x / xtiles) % strips;
+  const int b = blockIdx.x / (xtiles * strips);
+  const int lane = threadIdx.x & 31;
+  const int x = xt * (kFastThreads * 4) + threadIdx.x * 4;
+  const bool active = x < W;
+  const int y0 = 1 + strip * kFastRows;
+  const int yend = min(y0 + kFastRows, H - 1);
+  const uint8_t* base = img + size_t(b) * H * W;
+  const bool need_l = (lane == 0) && active && x > 0;
+  const bool need_r = (lane == 31) && active && (x + 4 < W);
+  bool inside[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) inside[c] = active && (x + c >= 1) && (x + c <= W - 2);
+
+  int top[6], mid[6], tsq[6], msq[6];
+  auto fetch = [&](int y, uint32_t& w, uint32_t& le, uint32_t& re) {
+    const uint8_t* row = base + size_t(y) * W;
+    w = active ? __ldg(reinterpret_cast<const uint32_t*>(row + x)) : 0u;
+    le = need_l ? uint32_t(__ldg(row + x - 1)) : 0u;
+    re = need_r ? uint32_t(__ldg(row + x + 4)) : 0u;
+  };
+  auto unpack = [&](uint32_t w, uint32_t le, uint32_t re, int (&v)[6]) {
+    const uint32_t lw = __shfl_up_sync(0xffffffffu, w, 1), rw = __shfl_down_sync(0xffffffffu, w, 1);
+    v[0] = int(lane == 0 ? le : (lw >> 24));
+    v[1] = int(w & 0xffu);
+    v[2] = int((w >> 8) & 0xffu);
+    v[3] = int((w >> 16) & 0xffu);
+    v[4] = int(w >> 24);
+    v[5] = int(lane == 31 ? re : (rw & 0xffu));
+  };
+  {
+    uint32_t w0, l0, r0, w1, l1, r1;
+    fetch(y0 - 1, w0, l0, r0);
+    fetch(y0, w1, l1, r1);
+    unpack(w0, l0, r0, top);
+    unpack(w1, l1, r1, mid);
+    if (WEIGHTED) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { tsq[c] = top[c] * top[c]; msq[c] = mid[c] * mid[c]; }
+    }
+  }
+  int acc_r = 0, acc_l1 = 0, acc_n = 0;
+  float facc_r = 0.f, facc_w = 0.f;
+
+  for (int yc = y0; yc < yend; yc += 6) {
+    uint32_t w[6], le[6], re[6];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) fetch(min(yc + r + 1, H - 1), w[r], le[r], re[r]);
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      int bot[6], bsq[6];
+      unpack(w[r], le[r], re[r], bot);
+      if (yc + r < yend) {
+        int vs[6], vq[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) vs[c] = top[c] + bot[c];
+        if (WEIGHTED) {
+#pragma unroll
+          for (int c = 0; c < 6; ++c) { bsq[c] = bot[c] * bot[c]; vq[c] = tsq[c] + bsq[c]; }
+        }
+#pragma unroll
+        for (int c = 1; c <= 4; ++c) {
+          const int xc = mid[c];
+          const int s8 = vs[c - 1] + vs[c] + vs[c + 1] + mid[c - 1] + mid[c + 1];   // 8-neighbour sum
+          int e;                                                                     // scaled residual x - x_hat
+          if (KIND == PRED_KB) e = 4 * xc - (2 * (vs[c] + mid[c - 1] + mid[c + 1]) - (vs[c - 1] + vs[c + 1]));
+          else e = 8 * xc - s8;
+          const int de = (xc & 1) ? e : -e;                                          // (x - x_bar) * (x - x_hat), scaled
+          if (inside[c - 1]) {
+            acc_l1 += abs(e);
+            if (WEIGHTED) {
+              const int q8 = vq[c - 1] + vq[c] + vq[c + 1] + msq[c - 1] + msq[c + 1];
+              const float wgt = ws_weight(WEIGHTED, float(s8), float(q8));
+              facc_r = fmaf(wgt, float(de), facc_r);
+              facc_w += wgt;
+            } else {
+              acc_r += de;
+              acc_n += 1;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) { top[c] = mid[c]; mid[c] = bot[c]; }
+      if (WEIGHTED) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) { tsq[c] = msq[c]; msq[c] = bsq[c]; }
+      }
+    }
+  }
+  constexpr float kScale = (KIND == PRED_KB) ? 0.25f : 0.125f;
+  __shared__ int ired[kFastThreads / 32][3];
+  __shared__ float fred[kFastThreads / 32][2];
+  const int warp = threadIdx.x >> 5;
+  const int r0 = __reduce_add_sync(0xffffffffu, acc_r), r1 = __reduce_add_sync(0xffffffffu, acc_l1),
+            r2 = __reduce_add_sync(0xffffffffu, acc_n);
+  const float f0 = warp_sum(facc_r), f1 = warp_sum(facc_w);
+  if (lane == 0) {
+    ired[warp][0] = r0; ired[warp][1] = r1; ired[warp][2] = r2;
+    fred[warp][0] = f0; fred[warp][1] = f1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int sr = 0, sl = 0, sn = 0;
+    float fr = 0.f, fw = 0.f;
+    for (int i = 0; i < kFastThreads / 32; ++i) { sr += ired[i][0]; sl += ired[i][1]; sn += ired[i][2]; fr += fred[i][0]; fw += fred[i][1]; }
+    float* dst = partials + (size_t(b) * strips * xtiles + size_t(strip) * xtiles + xt) * 2 * kPartialSlots;
+    // integers split into a multiple of 4096 and a 12-bit remainder: both exact in fp32, summed in double by finalize
+    const int sr_lo = sr & 0xfff, sl_lo = sl & 0xfff;
+    dst[0] = WEIGHTED ? fr * kScale : float(sr - sr_lo) * kScale;
+    dst[1] = WEIGHTED ? fw : float(sn);
+    dst[2] = float(sl - sl_lo) * kScale;
+    dst[3] = 0.f;
+    dst[4] = WEIGHTED ? 0.f : float(sr_lo) * kScale;
+    dst[5] = 0.f;
+    dst[6] = float(sl_lo) * kScale;
+    dst[7] = 0.f;
   }
 }
 
@@ -313,17 +520,57 @@ __global__ void unpack_kernel(Act src, float* __restrict__ dst, int with_halo) {
 
 cudaError_t launch_first_conv(const void* img, int img_is_float, int cin, const float* w, const float* bias, Act out,
                               cudaStream_t stream) {
+  if (cin == 1) {
+    const int segs = (out.W + kE11Seg - 1) / kE11Seg;
+    const int groups = (out.H + kE11Rows - 1) / kE11Rows;
+    const int grid = out.B * groups * segs;
+    if (img_is_float)
+      first_conv_kernel<true, 1><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);
+    else
+      first_conv_kernel<false, 1><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);
+    return cudaGetLastError();
+  }
   const size_t threads = size_t(out.B) * out.H * out.W * 8;
   const int grid = int((threads + 255) / 256);
   const size_t smem = (64 * cin * 9 + 64) * sizeof(float);
   if (img_is_float)
-    first_conv_kernel<true><<<grid, 256, smem, stream>>>(img, cin, w, bias, out);
+    first_conv_generic_kernel<true><<<grid, 256, smem, stream>>>(img, cin, w, bias, out);
   else
-    first_conv_kernel<false><<<grid, 256, smem, stream>>>(img, cin, w, bias, out);
+    first_conv_generic_kernel<false><<<grid, 256, smem, stream>>>(img, cin, w, bias, out);
   return cudaGetLastError();
 }
 
 int filter_ws_strips(int H) { return (H - 2 + kStripRows - 1) / kStripRows; }
+
+bool filter_ws_fast_ok(const void* img, int img_is_float, int W, int kind, int want_bias, const float* xhat_out) {
+  return !img_is_float && !want_bias && !xhat_out && (kind == PRED_KB || kind == PRED_AVG) && (W % 4 == 0) &&
+         (reinterpret_cast<uintptr_t>(img) % 4 == 0);
+}
+int filter_ws_fast_records(int H, int W) {
+  return ((H - 2 + kFastRows - 1) / kFastRows) * ((W + kFastThreads * 4 - 1) / (kFastThreads * 4)) * 2;
+}
+
+template <int KIND>
+static void launch_fast_kind(const uint8_t* img, int B, int H, int W, int weighted, float* partials, int strips, int xtiles,
+                             cudaStream_t stream) {
+  const int grid = B * strips * xtiles;
+  if (weighted == WS_UNWEIGHTED)
+    filter_ws_fast_kernel<KIND, WS_UNWEIGHTED><<<grid, kFastThreads, 0, stream>>>(img, H, W, partials, strips, xtiles);
+  else if (weighted == WS_WEIGHTED)
+    filter_ws_fast_kernel<KIND, WS_WEIGHTED><<<grid, kFastThreads, 0, stream>>>(img, H, W, partials, strips, xtiles);
+  else
+    filter_ws_fast_kernel<KIND, WS_ANTIWEIGHTED><<<grid, kFastThreads, 0, stream>>>(img, H, W, partials, strips, xtiles);
+}
+
+cudaError_t launch_filter_ws_fast(const void* img, int B, int H, int W, int kind, int weighted, float* partials,
+                                  cudaStream_t stream) {
+  const int strips = (H - 2 + kFastRows - 1) / kFastRows;
+  const int xtiles = (W + kFastThreads * 4 - 1) / (kFastThreads * 4);
+  const uint8_t* im = static_cast<const uint8_t*>(img);
+  if (kind == PRED_KB) launch_fast_kind<PRED_KB>(im, B, H, W, weighted, partials, strips, xtiles, stream);
+  else launch_fast_kind<PRED_AVG>(im, B, H, W, weighted, partials, strips, xtiles, stream);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_filter_ws(const void* img, int img_is_float, int B, int H, int W, int kind, int weighted, int want_bias,
                              float* xhat_out, float* partials, cudaStream_t stream) {

@@ -8,6 +8,11 @@ namespace wsu {
 cudaError_t launch_first_conv(const void* img, int img_is_float, int cin, const float* w, const float* bias, Act out,
                               cudaStream_t stream);
 int filter_ws_strips(int H);
+// register sliding-window fast path (uint8, KB/AVG, no bias term, no x_hat output, W % 4 == 0)
+bool filter_ws_fast_ok(const void* img, int img_is_float, int W, int kind, int want_bias, const float* xhat_out);
+int filter_ws_fast_records(int H, int W);  // partial records per image written by the fast kernel
+cudaError_t launch_filter_ws_fast(const void* img, int B, int H, int W, int kind, int weighted, float* partials,
+                                  cudaStream_t stream);
 cudaError_t launch_filter_ws(const void* img, int img_is_float, int B, int H, int W, int kind, int weighted, int want_bias,
                              float* xhat_out, float* partials, cudaStream_t stream);
 cudaError_t launch_ws_from_pred(const void* img, int img_is_float, const float* xhat, int xhat_cropped, const float* xbias,

@@ -29,12 +29,16 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 }
 
 // pack two floats as hi-parts / lo-parts bf16x2 words (element 0 in the low half).
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;  // one packed round-to-nearest-even conversion: upper half <- hi_elem, lower half <- lo_elem
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
 __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
-  __nv_bfloat16 ah, al, bh, bl;
-  split_bf16(a, ah, al);
-  split_bf16(b, bh, bl);
-  hi2 = uint32_t(__bfloat16_as_ushort(ah)) | (uint32_t(__bfloat16_as_ushort(bh)) << 16);
-  lo2 = uint32_t(__bfloat16_as_ushort(al)) | (uint32_t(__bfloat16_as_ushort(bl)) << 16);
+  hi2 = cvt_bf16x2(a, b);
+  const float ah = __uint_as_float(hi2 << 16);
+  const float bh = __uint_as_float(hi2 & 0xffff0000u);
+  lo2 = cvt_bf16x2(a - ah, b - bh);  // a - ah is exact in fp32 (Sterbenz-like: ah is a rounded to 8 bits)
 }
 
 // Reflect-halo targets of a logical coordinate v in [0,n): storage index v+1, plus the mirrored border

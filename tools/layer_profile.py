@@ -42,6 +42,7 @@ def main():
     res = {}
     for halo in (1, 0):
         lib.wsu_set_option(h, b'halo', halo)
+        lib.wsu_set_option(h, b'upconv_resident', halo)
         beta = W.ws_estimate(imgs, model)
         res[halo] = (profile(model, imgs, lib, h, reps), beta)
     print('beta halo==per-tap bit-equal:', torch.equal(res[1][1], res[0][1]), ' max|d| =', (res[1][1] - res[0][1]).abs().max().item())

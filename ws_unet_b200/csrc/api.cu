@@ -100,6 +100,8 @@ struct LayerW {  // device-side packed weights of one tensor-core layer
   uint8_t* wpack = nullptr;
   float* bias = nullptr;
   int cin = 0, cout = 0, n_tile = 0, ntaps = 0, npos = 0;
+  uint8_t* wres = nullptr;  // transposed conv only: phase-stacked tiles for the resident-weight kernel (may stay null)
+  int res_ntile = 0, res_cot = 0;
 };
 
 struct Plan {  // everything that depends on (micro-batch, H, W)
@@ -110,6 +112,8 @@ struct Plan {  // everything that depends on (micro-batch, H, W)
   int tiles_per_img = 0;
   std::vector<std::pair<ConvParams, std::pair<int, int>>> convs;  // params, (n_tile, epi); head is the last entry
   std::vector<std::string> conv_names;
+  std::vector<UpconvParams> ups;   // resident-weight up-convolutions
+  std::vector<int> up_idx;         // per conv step: index into ups or -1
 };
 
 }  // namespace
@@ -137,6 +141,7 @@ struct wsu_context {
   std::vector<std::string> prof_names;
   int prof_n = 0;
   int last_nimg = 0;  // images in the last micro-batch that ran
+  bool use_upres = true;  // transposed convs through upconv_res_kernel (option "upconv_resident")
   bool use_halo = true;  // 3x3 layers through conv_halo_kernel (option "halo"; 0 = per-tap reload kernel, for A/B runs)
 };
 
@@ -232,6 +237,26 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   }
   pl.convs.push_back({p, {lw.n_tile, epi}});
   pl.conv_names.push_back(lname);
+  int ui = -1;
+  if (upsample && lw.wres && out) {
+    UpconvParams u;
+    std::memset(&u, 0, sizeof(u));
+    rc = make_act_tmap(&u.tmapA, src0, 16, 8);
+    if (rc) return rc;
+    u.wres = lw.wres;
+    u.bias = lw.bias;
+    u.cblocks = lw.cin / 64;
+    u.co_t = lw.res_cot;
+    u.n_tiles = lw.cout / lw.res_cot;
+    u.B = src0.B; u.H = src0.H; u.W = src0.W;
+    u.tiles_x = (u.W + 15) / 16;
+    u.tiles_y = (u.H + 7) / 8;
+    u.total_boxes = u.B * u.tiles_x * u.tiles_y;
+    u.out = *out;
+    ui = int(pl.ups.size());
+    pl.ups.push_back(u);
+  }
+  pl.up_idx.push_back(ui);
   return WSU_OK;
 }
 
@@ -366,7 +391,11 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
       p.crop = crop;
     }
     mark(i + 1);
-    if (halo)
+    if (pl.up_idx[i] >= 0 && h->use_upres) {
+      UpconvParams u = pl.ups[pl.up_idx[i]];
+      if (nimg != pl.mb) { u.B = nimg; u.total_boxes = nimg * u.tiles_x * u.tiles_y; }
+      LAUNCH_TRY(launch_upconv_res(u, 4 * u.co_t, h->num_sms, st));
+    } else if (halo)
       LAUNCH_TRY(launch_conv_halo(p, n_tile, epi, h->num_sms, st));
     else
       LAUNCH_TRY(launch_conv_mma(p, n_tile, epi, h->num_sms, st));
@@ -463,7 +492,7 @@ int wsu_destroy(wsu_handle h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   free_plan(h->plan.get());
-  for (auto& kv : h->layers) { cudaFree(kv.second.wpack); cudaFree(kv.second.bias); }
+  for (auto& kv : h->layers) { cudaFree(kv.second.wpack); cudaFree(kv.second.bias); cudaFree(kv.second.wres); }
   cudaFree(h->e11_w);
   cudaFree(h->e11_b);
   for (int i = 0; i < 2; ++i) {
@@ -484,6 +513,10 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
   if (!std::strcmp(key, "micro_batch")) {
     if (value < 0) return fail(WSU_ERR_INVALID, "micro_batch must be >= 0");
     h->micro_batch = value;
+    return WSU_OK;
+  }
+  if (!std::strcmp(key, "upconv_resident")) {
+    h->use_upres = value != 0;
     return WSU_OK;
   }
   if (!std::strcmp(key, "halo")) {
@@ -563,8 +596,36 @@ static int upload_layer(wsu_context* h, const std::string& name, int cin, int co
               std::memcpy(lo + sw128_off(n, k), &vl, 2);
             }
         }
+  if (transposed) {
+    // phase-stacked resident layout: largest co_t in {64, 32} whose (hi, lo) tiles fit kUpconvResBytes
+    for (int cot : {64, 32}) {
+      const int ntile = 4 * cot;
+      if (cout % cot == 0 && cblocks * ntile * 256 <= kUpconvResBytes) { lw.res_cot = cot; lw.res_ntile = ntile; break; }
+    }
+    if (lw.res_cot) {
+      const int rt = cout / lw.res_cot;
+      const size_t tile = size_t(lw.res_ntile) * 128;
+      std::vector<uint8_t> res(size_t(rt) * cblocks * 2 * tile, 0);
+      for (int nt = 0; nt < rt; ++nt)
+        for (int c = 0; c < cblocks; ++c) {
+          uint8_t* hi = res.data() + (size_t(nt) * cblocks + c) * 2 * tile;
+          uint8_t* lo = hi + tile;
+          for (int r = 0; r < lw.res_ntile; ++r)
+            for (int k = 0; k < 64; ++k) {
+              const int pos = r / lw.res_cot, co = nt * lw.res_cot + r % lw.res_cot, ci = c * 64 + k;
+              const float v = w->data[((size_t(ci) * cout + co) * 2 + (pos >> 1)) * 2 + (pos & 1)];
+              const uint16_t vh = f2bf(v);
+              const uint16_t vl = f2bf(v - bf2f(vh));
+              std::memcpy(hi + sw128_off(r, k), &vh, 2);
+              std::memcpy(lo + sw128_off(r, k), &vl, 2);
+            }
+        }
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&lw.wres), res.size()));
+      CUDA_TRY(cudaMemcpy(lw.wres, res.data(), res.size(), cudaMemcpyHostToDevice));
+    }
+  }
   auto old = h->layers.find(name);
-  if (old != h->layers.end()) { cudaFree(old->second.wpack); cudaFree(old->second.bias); }
+  if (old != h->layers.end()) { cudaFree(old->second.wpack); cudaFree(old->second.bias); cudaFree(old->second.wres); }
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&lw.wpack), pack.size()));
   CUDA_TRY(cudaMemcpy(lw.wpack, pack.data(), pack.size(), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&lw.bias), size_t(cout) * 4));

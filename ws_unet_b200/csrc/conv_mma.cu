@@ -24,14 +24,17 @@ namespace {
 constexpr int kThreads = 320;          // warps: 0 TMA, 1 MMA, 2..9 epilogue (two groups of four lane quadrants)
 constexpr int kABytes = 2 * 128 * 128;  // hi + lo tile of 128 pixels x 64 channels
 constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
+constexpr int kScratchPitch = 80;                       // 64 B of payload + 16 B pad: conflict-free 16-byte writes
+constexpr int kScratchPerWarp = 32 * kScratchPitch;     // 2560 B of epilogue staging per warp
+constexpr int kScratchBytes = 8 * kScratchPerWarp;      // eight epilogue warps
 
 template <int N_TILE>
 struct Cfg {
   static constexpr int M_SUB = kAccCols / N_TILE;          // pixel boxes sharing one weight chunk
   static constexpr int W_BYTES = wchunk_bytes(N_TILE);
-  static constexpr int SA = (N_TILE == 64) ? 5 : 4;        // A ring depth
+  static constexpr int SA = 4;                             // A ring depth
   static constexpr int SW = (N_TILE == 64) ? 3 : 2;        // W ring depth
-  static constexpr int SMEM = SA * kABytes + SW * W_BYTES + 1024 /*align*/ + 4096 /*bias*/ + 256 /*barriers*/;
+  static constexpr int SMEM = SA * kABytes + SW * W_BYTES + kScratchBytes + 1024 /*align*/ + 4096 /*bias*/ + 256 /*barriers*/;
 };
 
 struct TileCoord {
@@ -76,6 +79,53 @@ __device__ __forceinline__ void store_pixel32(const Act& o, int b, int oy, int o
 
 // Epilogue of one 128-pixel box: thread owns pixel (y, x) = TMEM lane; tbase addresses its accumulator columns.
 // pool_xor: lane distance of the vertical 2x2-pool partner (= box width in pixels).
+// Geometry of the 128-pixel box a warp is finishing: row r of the box <-> pixel (y0 + (r >> tw_shift), x0 + (r & mask)).
+struct BoxGeo {
+  int b, y0, x0, tw_shift, H, W;  // H, W: bounds of the GEMM pixel grid (input dims)
+  int up, pos;                    // up = 1: output pixel (2y + pos/2, 2x + pos%2) of a 2x upsampled map
+  __device__ __forceinline__ bool pixel(int row, int& oy, int& ox) const {
+    const int y = y0 + (row >> tw_shift), x = x0 + (row & ((1 << tw_shift) - 1));
+    oy = up ? 2 * y + (pos >> 1) : y;
+    ox = up ? 2 * x + (pos & 1) : x;
+    return (y < H) && (x < W);
+  }
+};
+
+// Warp-cooperative store of one 32-channel chunk of the warp's 32 pixels. Registers hold "my pixel, 32 channels";
+// a 64-byte row per pixel is staged in shared memory and re-read so that 4 consecutive lanes write the 4 consecutive
+// 16-byte pieces of one pixel: a store instruction then touches 8 half-lines instead of 32 different lines
+// (uncoalesced 16-byte stores made the LSU, not the tensor pipe, the limiter of the store-heavy layers).
+__device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scratch, int lane, int row0, int c0,
+                                                      const uint32_t (&h)[16], const uint32_t (&l)[16], const BoxGeo& g) {
+  const int piece = lane & 3;
+#pragma unroll
+  for (int plane = 0; plane < 2; ++plane) {
+    __syncwarp();
+    uint4* mine = reinterpret_cast<uint4*>(scratch + lane * kScratchPitch);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      mine[q] = plane ? make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3])
+                      : make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    __syncwarp();
+    __nv_bfloat16* base = o.base + (plane ? o.plane : 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = (lane >> 2) + 8 * i;
+      const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * kScratchPitch + piece * 16);
+      int oy, ox;
+      if (g.pixel(row0 + q, oy, ox)) {
+        int ys[3], xs[3];
+        const int ny = halo_targets(oy, o.H, ys), nx = halo_targets(ox, o.W, xs);
+        for (int iy = 0; iy < ny; ++iy)
+          for (int ix = 0; ix < nx; ++ix) {
+            const size_t off = ((size_t(g.b) * (o.H + 2) + ys[iy]) * (o.W + 2) + xs[ix]) * o.C + c0 + piece * 8;
+            *reinterpret_cast<uint4*>(base + off) = v;
+          }
+      }
+    }
+  }
+}
+
 // STACKED (Cout = 64 layers of the halo kernel): the accumulator is 128 columns wide, columns [0,64) hold
 // (Ahi + Alo) * Whi and columns [64,128) hold Ahi * Wlo of the same 64 output channels; they are summed here.
 template <int N_TILE, int EPI, bool STACKED>
@@ -97,7 +147,8 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&f)[32]) {
 
 template <int N_TILE, int EPI, bool STACKED = false>
 __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* sBias, uint32_t tbase, int b, int y, int x,
-                                             bool valid, int nt, int pos, int tx, int ty, int pool_xor, WsAcc& acc) {
+                                             bool valid, int nt, int pos, int tx, int ty, int pool_xor, WsAcc& acc,
+                                             const BoxGeo& geo, uint8_t* scratch, int lane, int row0) {
         if constexpr (EPI == EPI_ACT) {
 #pragma unroll 1
           for (int cc = 0; cc < N_TILE / 32; ++cc) {
@@ -112,11 +163,7 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
             uint32_t h[16], l[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
-            if (valid) {
-              const int oy = p.upsample ? 2 * y + (pos >> 1) : y;
-              const int ox = p.upsample ? 2 * x + (pos & 1) : x;
-              store_pixel32(p.out, b, oy, ox, n0, h, l);
-            }
+            store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo);
             if (p.do_pool) {
               // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16)
 #pragma unroll
@@ -195,7 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                                   // SA x 32 KB
   uint8_t* sW = smem + C::SA * kABytes;                 // SW x W_BYTES
-  float* sBias = reinterpret_cast<float*>(sW + C::SW * C::W_BYTES);  // up to 1024 floats
+  uint8_t* sScratch = sW + C::SW * C::W_BYTES;          // epilogue store staging
+  float* sBias = reinterpret_cast<float*>(sScratch + kScratchBytes);  // up to 1024 floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + 4096);
   uint64_t* a_full = bars;                 // [SA]
   uint64_t* a_empty = a_full + C::SA;      // [SA]
@@ -312,7 +360,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_cons
         const int x = t.x0 + j * p.TW + tx;
         const bool valid = (y < p.H) && (x < p.W);
         const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acs * kAccCols + j * N_TILE);
-        epilogue_box<N_TILE, EPI>(p, sBias, tbase, t.b, y, x, valid, t.nt, t.pos, tx, ty, p.TW, acc);
+        const BoxGeo geo{t.b, t.y0, t.x0 + j * p.TW, 4, p.H, p.W, p.upsample, t.pos};
+        epilogue_box<N_TILE, EPI>(p, sBias, tbase, t.b, y, x, valid, t.nt, t.pos, tx, ty, p.TW, acc, geo,
+                                  sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32);
       }
       // all TMEM reads of this stage are complete -> hand the accumulators back to the MMA warp
       tc_fence_before();
@@ -375,9 +425,9 @@ struct HCfg {
   static constexpr int W_BYTES = STACKED ? 2 * N_TILE * 128  // ring slot: whole (hi, lo) chunk, contiguous
                                          : N_TILE * 128;     //            or one plane of one tap
   static constexpr int W_PER_TAP = STACKED ? 1 : 2;          // ring slots consumed per tap
-  static constexpr int SW = STACKED ? 4 : 5;
+  static constexpr int SW = 4;
   static constexpr int BIAS_BYTES = (N_TILE == 64) ? 256 : 4096;
-  static constexpr int SMEM = SA * kHaloABytes + SW * W_BYTES + 1024 + BIAS_BYTES + 256;
+  static constexpr int SMEM = SA * kHaloABytes + SW * W_BYTES + kScratchBytes + 1024 + BIAS_BYTES + 256;
 };
 
 struct BoxCoord {
@@ -404,7 +454,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sW = smem + C::SA * kHaloABytes;
-  float* sBias = reinterpret_cast<float*>(sW + C::SW * C::W_BYTES);
+  uint8_t* sScratch = sW + C::SW * C::W_BYTES;
+  float* sBias = reinterpret_cast<float*>(sScratch + kScratchBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + C::BIAS_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + C::SA;
@@ -558,7 +609,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const bool valid = (y < p.H) && (x < p.W);
         const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acs * kAccCols + j * C::ACC_W);
         WsAcc acc;
-        epilogue_box<N_TILE, EPI, C::STACKED>(p, sBias, tbase, bc.b, y, x, valid, nt, 0, tx, ty, kHaloTW, acc);
+        const BoxGeo geo{bc.b, bc.y0, bc.x0, 3, p.H, p.W, 0, 0};
+        epilogue_box<N_TILE, EPI, C::STACKED>(p, sBias, tbase, bc.b, y, x, valid, nt, 0, tx, ty, kHaloTW, acc, geo,
+                                              sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32);
         if constexpr (EPI == EPI_HEAD) {
           if (p.partials) {
             const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1);
@@ -595,6 +648,146 @@ cudaError_t launch_halo_t(const ConvParams& p, int num_sms, cudaStream_t stream)
   return cudaGetLastError();
 }
 
+
+// ================================================================================================ resident-weight upconv
+// ConvTranspose2d(k=2, s=2) (unet.py:177,183): out[2y+dy][2x+dx][co] = b[co] + sum_ci in[y][x][ci] * w[ci][co][dy][dx].
+// The four phases are stacked along N and the whole (hi, lo) weight set of the CTA's N tile (128 KB) stays in shared
+// memory, so each activation box is read exactly once per N tile and the kernel is bound by its output writes.
+constexpr int kUpThreads = 320;
+constexpr int kUpSA = 2;
+
+template <int N_TILE>
+__global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_constant__ UpconvParams p) {
+  constexpr int kBoxBytes = kABytes;  // 32 KB: hi + lo tile of 128 pixels x 64 channels
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;                       // cblocks x (hi | lo) x N_TILE rows x 128 B  (<= 128 KB)
+  uint8_t* sA = smem + kUpconvResBytes;     // kUpSA x 32 KB
+  uint8_t* sScratch = sA + kUpSA * kBoxBytes;
+  float* sBias = reinterpret_cast<float*>(sScratch + kScratchBytes);   // co_t floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + 256);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kUpSA;
+  uint64_t* acc_full = a_empty + kUpSA;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* w_bar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nt = blockIdx.x % p.n_tiles;
+  const int first_box = blockIdx.x / p.n_tiles;
+  const int box_step = gridDim.x / p.n_tiles;
+  const uint32_t w_tile_bytes = N_TILE * 128;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmapA);
+    for (int i = 0; i < kUpSA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int i = threadIdx.x; i < p.co_t; i += kUpThreads) sBias[i] = p.bias[nt * p.co_t + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // weights of this N tile: resident for the whole kernel
+      const uint32_t wbytes = uint32_t(p.cblocks) * 2 * w_tile_bytes;
+      const uint8_t* wsrc = p.wres + size_t(nt) * wbytes;
+      mbar_arrive_expect_tx(w_bar, wbytes);
+      for (int i = 0; i < p.cblocks * 2; ++i) bulk_load(sW + i * w_tile_bytes, wsrc + size_t(i) * w_tile_bytes, w_tile_bytes, w_bar);
+      int as = 0;
+      uint32_t aph = 0;
+      for (int box = first_box; box < p.total_boxes; box += box_step) {
+        const int tx = box % p.tiles_x, r = box / p.tiles_x;
+        const int ty = r % p.tiles_y, b = r / p.tiles_y;
+        for (int c = 0; c < p.cblocks; ++c) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          mbar_arrive_expect_tx(&a_full[as], kBoxBytes);
+          tma_load_5d(sA + as * kBoxBytes, &p.tmapA, &a_full[as], c * 64, tx * 16 + 1, ty * 8 + 1, b, 0);
+          if (++as == kUpSA) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(N_TILE);
+      int as = 0, acs = 0;
+      uint32_t aph = 0, acph = 0;
+      mbar_wait(w_bar, 0);
+      for (int box = first_box; box < p.total_boxes; box += box_step) {
+        mbar_wait(&acc_empty[acs], acph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + uint32_t(acs * kAccCols);
+        for (int c = 0; c < p.cblocks; ++c) {
+          mbar_wait(&a_full[as], aph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(sA + as * kBoxBytes), a_lo = a_hi + 128 * 128;
+          const uint32_t w_hi = smem_u32(sW) + uint32_t(c) * 2 * w_tile_bytes, w_lo = w_hi + w_tile_bytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da_hi = make_sw128_desc(a_hi + k * 32), da_lo = make_sw128_desc(a_lo + k * 32);
+            const uint64_t dw_hi = make_sw128_desc(w_hi + k * 32), dw_lo = make_sw128_desc(w_lo + k * 32);
+            umma_bf16(d, da_hi, dw_hi, idesc, (c | k) != 0);
+            umma_bf16(d, da_lo, dw_hi, idesc, 1);
+            umma_bf16(d, da_hi, dw_lo, idesc, 1);
+          }
+          umma_commit(&a_empty[as]);
+          if (++as == kUpSA) { as = 0; aph ^= 1; }
+        }
+        umma_commit(&acc_full[acs]);
+        if (++acs == 2) { acs = 0; acph ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3, grp = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int ty_in = row >> 4, tx_in = row & 15;
+    int acs = 0;
+    uint32_t acph = 0;
+    constexpr int kChunks = N_TILE / 32;
+    for (int box = first_box; box < p.total_boxes; box += box_step) {
+      const int tx = box % p.tiles_x, r = box / p.tiles_x;
+      const int ty = r % p.tiles_y, b = r / p.tiles_y;
+      const int y = ty * 8 + ty_in, x = tx * 16 + tx_in;
+      const bool valid = (y < p.H) && (x < p.W);
+      mbar_wait(&acc_full[acs], acph);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acs * kAccCols);
+#pragma unroll 1
+      for (int cc = grp * (kChunks / 2); cc < (grp + 1) * (kChunks / 2); ++cc) {
+        uint32_t v[32];
+        tmem_ld32(tbase + cc * 32, v);
+        tmem_ld_wait();
+        const int col0 = cc * 32;
+        const int pos = col0 / p.co_t, cl = col0 % p.co_t;
+        uint32_t h[16], l[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          split_pack2(__uint_as_float(v[2 * i]) + sBias[cl + 2 * i], __uint_as_float(v[2 * i + 1]) + sBias[cl + 2 * i + 1], h[i], l[i]);
+        const BoxGeo geo{b, ty * 8, tx * 16, 4, p.H, p.W, 1, pos};
+        store_chunk_coalesced(p.out, sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32, nt * p.co_t + cl, h, l, geo);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acs]);
+      if (++acs == 2) { acs = 0; acph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+constexpr int kUpSmem = kUpconvResBytes + kUpSA * kABytes + kScratchBytes + 1024 + 256 + 256;
+
 }  // namespace
 
 cudaError_t conv_mma_init() {
@@ -610,6 +803,10 @@ cudaError_t conv_mma_init() {
   e = cudaFuncSetAttribute(conv_halo_kernel<128, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<128>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<64>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upconv_res_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upconv_res_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
   return e;
 }
 
@@ -637,5 +834,19 @@ cudaError_t launch_conv_halo(const ConvParams& p, int n_tile, int epi, int num_s
   if (n_tile == 64) return p.n_tiles == 1 ? launch_halo_t<64, EPI_ACT>(p, num_sms, stream) : cudaErrorInvalidValue;
   if (n_tile == 128) return launch_halo_t<128, EPI_ACT>(p, num_sms, stream);
   return cudaErrorInvalidValue;
+}
+}  // namespace wsu
+
+namespace wsu {
+cudaError_t launch_upconv_res(const UpconvParams& p, int n_tile, int num_sms, cudaStream_t stream) {
+  if (p.cblocks * n_tile * 256 > kUpconvResBytes || n_tile != 4 * p.co_t) return cudaErrorInvalidValue;
+  int grid = (num_sms / p.n_tiles) * p.n_tiles;
+  const int max_useful = p.total_boxes * p.n_tiles;
+  if (grid > max_useful) grid = max_useful;
+  if (grid <= 0) return cudaErrorInvalidValue;
+  if (n_tile == 256) upconv_res_kernel<256><<<grid, kUpThreads, kUpSmem, stream>>>(p);
+  else if (n_tile == 128) upconv_res_kernel<128><<<grid, kUpThreads, kUpSmem, stream>>>(p);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
 }
 }  // namespace wsu

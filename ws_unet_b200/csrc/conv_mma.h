@@ -57,6 +57,18 @@ cudaError_t launch_conv_mma(const ConvParams& p, int n_tile, int epi, int num_sm
 cudaError_t launch_conv_halo(const ConvParams& p, int n_tile, int epi, int num_sms, cudaStream_t stream);
 constexpr int halo_msub(int) { return 2; }
 constexpr int kHaloTW = 8, kHaloTH = 16;
+// Transposed convolution with shared-memory-resident weights: all 4 output phases stacked along N (N_TILE = 4 * co_t).
+struct alignas(64) UpconvParams {
+  CUtensorMap tmapA;      // source activation, box (64 ch, 16, 8, 1 img, 2 planes)
+  const uint8_t* wres;    // [n_tiles][cblocks][hi tile | lo tile], rows r -> (phase r / co_t, channel nt*co_t + r % co_t)
+  const float* bias;      // [Cout]
+  int cblocks, n_tiles, co_t;
+  int B, H, W;            // input dims
+  int tiles_x, tiles_y, total_boxes;
+  Act out;                // (2H, 2W) destination
+};
+cudaError_t launch_upconv_res(const UpconvParams& p, int n_tile, int num_sms, cudaStream_t stream);
+constexpr int kUpconvResBytes = 131072;  // weight bytes that must fit: cblocks * N_TILE * 256
 cudaError_t conv_mma_init();  // sets max dynamic shared memory on every instantiation
 
 }  // namespace wsu

@@ -1,0 +1,86 @@
+"""GPU: the 'next' rows of SURVEY.md section 8f - run()-compatible batched dataset driver (N1), WSLoss / WSMeter
+definitions (N2), ROC from beta_hat (N3)."""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import unet_oracle as uo
+from oracle import ws_oracle as wo
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_dataset(root, n=6, alpha=0.4, hw=(64, 96)):
+    from PIL import Image
+    from ws_unet_b200 import data as wdata
+    (root / 'images').mkdir(parents=True)
+    sdir = root / f'stego_LSBr_alpha_{alpha}_independent_images'   # on-disk spelling of the shipped data (F11)
+    sdir.mkdir()
+    rows_c, rows_s, imgs = [], [], {}
+    for i in range(n):
+        c = wdata.synthetic_cover(i, *hw)
+        s = wdata.embed_lsbr(c, alpha, i)
+        Image.fromarray(c.numpy()).save(root / 'images' / f'{i}.png')
+        Image.fromarray(s.numpy()).save(sdir / f'{i}.png')
+        rows_c.append(dict(name=f'images/{i}.png', height=hw[0], width=hw[1]))
+        rows_s.append(dict(name=f'stego_LSBR_alpha_{alpha}_independent_images/{i}.png', height=hw[0], width=hw[1],
+                           stego_method='LSBR', alpha=alpha))
+        imgs[f'images/{i}.png'], imgs[rows_s[-1]['name']] = c.numpy(), s.numpy()
+    pd.DataFrame(rows_c).to_csv(root / 'images' / 'files.csv', index=False)
+    pd.DataFrame(rows_s).to_csv(sdir / 'files.csv', index=False)
+    return imgs
+
+
+def test_run_matches_oracle_per_file(cuda_dev, tmp_path):
+    from ws_unet_b200 import dataset as D
+    import ws_unet_b200 as W
+    imgs = _write_dataset(tmp_path)
+    for stego, alpha in [(None, None), ('LSBR', 0.4)]:
+        for model_name, weighted in [('KB', 0), ('KB', 1), ('AVG', 1)]:
+            df = D.run(tmp_path, stego, alpha, model_name, channels=(3,), weighted=weighted, batch=4)
+            assert {'name', 'beta_hat', 'channels', 'weighted', 'correct_bias', 'model_name'} <= set(df.columns)
+            assert len(df) == 6 and (df['channels'] == '3').all()
+            for _, r in df.iterrows():
+                key = '/'.join(r['name'].split('/')[-2:])
+                ref = uo.ws_attack_c(imgs[key], kind={'KB': 0, 'AVG': 1}[model_name], weighted=weighted)[0]
+                assert abs(r['beta_hat'] - ref) < 1e-4
+    sd = uo.numpy_weights(2, seed=31)
+    m = W.get_model('unet_2', 1).to(cuda_dev)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    df = D.run(tmp_path, 'LSBR', 0.4, 'my_unet', predictor=m, weighted=0, batch=4)
+    assert (df['model_name'] == 'UNet').all()
+    for _, r in df.iterrows():
+        im = imgs['/'.join(r['name'].split('/')[-2:])]
+        xhat = uo.unet_forward(sd, (im.astype(np.float32) / np.float32(255.))[None, None], 2)[0, 0, 1:-1, 1:-1] * np.float32(255.)
+        assert abs(r['beta_hat'] - uo.ws_attack_c(im, xhat=xhat, weighted=0)[0]) < 1e-4
+
+
+def test_wsloss_wsmeter_match_reference_definitions(cuda_dev, ws_golden):
+    from ws_unet_b200.metrics import WSLoss, WSMeter, ws_betas_hat
+    xin = torch.from_numpy(ws_golden['wsloss_xin']).to(cuda_dev)
+    xout = torch.from_numpy(ws_golden['wsloss_xout']).to(cuda_dev)
+    got = ws_betas_hat(xout, xin, crop=0).cpu().numpy()
+    assert np.abs(got - ws_golden['wsloss_betas_hat']).max() < 1e-4      # reference WSLoss._error with betas = 0
+    alphas = torch.tensor([0.1, 0.2, 0.4])
+    loss = WSLoss()(xout, (None, alphas.to(cuda_dev)), xin).item()
+    assert abs(loss - np.mean(np.abs(ws_golden['wsloss_betas_hat'] - alphas.numpy() / 2))) < 1e-4
+    meter = WSMeter()
+    meter.update(ws_golden['wsloss_xin'], ws_golden['wsloss_xout'], alphas.numpy())
+    ref = wo.wsloss_betas(ws_golden['wsloss_xout'], ws_golden['wsloss_xin'], crop=1)
+    assert abs(meter.avg - np.mean(np.abs(ref - alphas.numpy() / 2))) < 1e-4
+
+
+def test_roc_from_gpu_beta_hat(cuda_dev):
+    """N3: the consumer of beta_hat. KB-WS on synthetic covers vs alpha=0.1 stego must separate almost perfectly."""
+    import ws_unet_b200 as W
+    from ws_unet_b200 import data as wdata
+    from ws_unet_b200.metrics import produce_roc
+    covers = wdata.synthetic_covers(24, 128, 128)
+    stego = torch.stack([wdata.embed_lsbr(covers[i, 0], 0.1, i) for i in range(24)])[:, None]
+    bc = W.ws_estimate(covers.to(cuda_dev), 'KB', weighted=1).cpu().numpy()
+    bs = W.ws_estimate(stego.to(cuda_dev), 'KB', weighted=1).cpu().numpy()
+    df = pd.DataFrame({'stego_method': ['Cover'] * 24 + ['LSBR'] * 24, 'model_name': 'KB', 'alpha': [0.] * 24 + [0.1] * 24,
+                       'beta_hat': np.concatenate([bc, bs])})
+    roc = produce_roc(df)
+    assert roc['auc'].iloc[0] > 0.95 and roc['p_e'].iloc[0] < 0.1

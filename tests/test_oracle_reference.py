@@ -56,3 +56,49 @@ def test_shipped_lsbr_semantics(alpha, rate):
         n += c.size
     assert abs(diffs / n - rate) < 2e-4             # measured rates, SURVEY.md section 4
     assert cover.dtype == np.uint8
+
+
+def _import_reference():
+    import importlib.util
+    import os
+    import sys
+    spec = importlib.util.spec_from_file_location('make_golden', pathlib.Path(__file__).parent / 'golden' / 'make_golden.py')
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    cwd = os.getcwd()
+    try:
+        return mg.import_reference()
+    finally:
+        os.chdir(cwd)
+        sys.path[:] = [p for p in sys.path if not p.startswith(str(REF))]
+
+
+def test_produce_roc_matches_reference(capsys):
+    import pandas as pd
+    from ws_unet_b200.metrics import produce_roc
+    _defs, rfilters, runet, rws = _import_reference()
+    rng = np.random.default_rng(3)
+    rows = []
+    for m in ['KB', 'UNet']:
+        for i in range(40):
+            rows.append(dict(stego_method='Cover', model_name=m, alpha=0., beta_hat=rng.normal(0, 0.02)))
+        for i in range(60):
+            rows.append(dict(stego_method='LSBR', model_name=m, alpha=0.05, beta_hat=rng.normal(0.025, 0.02)))
+    df = pd.DataFrame(rows)
+    ref = rws.roc.produce_roc(df).reset_index(drop=True)
+    got = produce_roc(df).reset_index(drop=True)
+    for col in ['tau', 'tpr', 'fpr', 'p_e', 'tau0', 'auc', 'fpr_50', 'tpr_50']:
+        assert np.allclose(ref[col].to_numpy(dtype=float), got[col].to_numpy(dtype=float), atol=1e-12), col
+    assert list(ref['label']) == list(got['label'])
+
+
+def test_list_files_matches_fabrika_selection():
+    from ws_unet_b200 import dataset as D
+    covers = D.list_files(REF / 'data')
+    assert covers['name'].tolist() == sorted(f'images/{i}.png' for i in range(6, 11))
+    st = D.list_files(REF / 'data', stego_method='LSBR', alpha=0.4)
+    assert len(st) == 5 and set(st['alpha']) == {0.4} and set(st['stego_method']) == {'LSBR'}
+    # files.csv says LSBR, the directory on disk is LSBr: paths must still resolve
+    assert all(D._resolve_case(REF / 'data' / n).exists() for n in st['name'])
+    st2 = D.list_files(REF / 'data', stego_method='HILLR', alpha=0.05, take_num_images=2)
+    assert len(st2) == 2

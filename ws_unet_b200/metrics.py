@@ -1,0 +1,82 @@
+"""Consumers of the beta_hat vector and the batched training-side definitions, mirrored from the reference:
+  * WSLoss / WSMeter  - src/_defs/losses.py:45-89, src/_defs/metrics.py:116-142 (forward values only; no autograd)
+  * produce_roc       - src/ws/roc.py:198-283 (501-threshold ROC, AUC, P_E from beta_hat)
+The WS arithmetic runs through libwsunet (wsu_ws_from_prediction); ROC is a few thousand scalar ops on the host.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import ws
+
+
+def ws_betas_hat(outputs: torch.Tensor, inputs: torch.Tensor, crop: int = 0) -> torch.Tensor:
+    """betas_hat of WSLoss._error (crop=0, relu; losses.py:46-61) or WSMeter.update (crop=1, clip; metrics.py:122-137):
+    images (B,1,H,W) float32 in [0,1] on a CUDA device; outputs = predictor output in [0,1]."""
+    return ws.ws_from_prediction(inputs, outputs[:, 0] * 255., weighted=0, clip=True, crop=crop)
+
+
+class WSLoss:
+    """Forward value of src/_defs/losses.py:45-89: mean |relu(beta_hat) - alpha/2| over the batch."""
+
+    def _error(self, outputs, inputs, betas):
+        return torch.abs(ws_betas_hat(outputs, inputs, crop=0) - betas.to(outputs.device))
+
+    def __call__(self, outputs, targets, inputs):
+        _, alphas = targets
+        return torch.mean(self._error(outputs, inputs, alphas / 2.))
+
+
+class WSMeter:
+    """src/_defs/metrics.py:116-142 (AverageMeter over per-batch mean |beta_hat - alpha/2|, 1-px crop)."""
+    name = 'ws'
+
+    def __init__(self):
+        self.sum, self.count = 0.0, 0
+
+    def update(self, x, x_hat, alphas):
+        x = torch.as_tensor(x)
+        x_hat = torch.as_tensor(x_hat)
+        if not x.is_cuda:
+            x, x_hat = x.cuda(), x_hat.cuda()
+        betas_hat = ws_betas_hat(x_hat, x, crop=1).cpu().numpy()
+        self.sum += float(np.mean(np.abs(betas_hat - np.asarray(alphas) / 2.)))
+        self.count += 1
+
+    @property
+    def avg(self):
+        return self.sum / max(self.count, 1)
+
+
+def produce_roc(df_ws: pd.DataFrame) -> pd.DataFrame:
+    """src/ws/roc.py:198-283 for WS estimators: per (stego_method, model_name) against the 'Cover' rows, thresholds
+    tau in linspace(0,1,501) on clip(beta_hat, 0), AUC by the reference's FPR-bin weighting, P_E = min (1-TPR+FPR)/2."""
+    out = []
+    for (stego_method, model_name), _ in df_ws.groupby(['stego_method', 'model_name']):
+        if stego_method == 'Cover':
+            continue
+        d = df_ws[(df_ws['model_name'] == model_name) & df_ws['stego_method'].isin([stego_method, 'Cover'])]
+        y_hat = np.clip(d['beta_hat'].to_numpy(), 0, None)
+        y = d['alpha'].to_numpy() / 2
+        taus = np.array(list(reversed(np.linspace(0, 1, 501, endpoint=True))))
+        gt = y_hat[None, :] > taus[:, None]
+        pos, neg = (y > 0.)[None, :], (y <= 0.)[None, :]
+        TP, FP = (gt & pos).sum(1), (gt & neg).sum(1)
+        TN, FN = (~gt & neg).sum(1), (~gt & pos).sum(1)
+        tpr, fpr = TP / (TP + FN), FP / (FP + TN)
+        bins = np.diff(fpr, prepend=fpr[0])
+        bins = bins / bins.sum()
+        auc = np.sum(bins * tpr)
+        err = (1 - tpr + fpr) / 2
+        i0 = int(np.argmin(err))
+        g50 = y_hat > .5
+        fpr50 = (g50 & (y <= 0.)).sum() / max(((y <= 0.)).sum(), 1)
+        tpr50 = (g50 & (y > 0.)).sum() / max(((y > 0.)).sum(), 1)
+        out.append(pd.DataFrame({
+            'stego_method': stego_method, 'model_name': model_name, 'tau': taus, 'tpr': tpr, 'fpr': fpr, 'p_e': err[i0],
+            'tau0': taus[i0], 'fpr_tau0': fpr[i0], 'tpr_tau0': tpr[i0], 'auc': auc, 'fpr_50': fpr50, 'tpr_50': tpr50,
+            'label': f'WS-{model_name}',
+        }))
+    return pd.concat(out)

@@ -18,19 +18,31 @@ from .. import _native
 
 
 class UniformDropout(nn.Module):
-    """Input dropout of the reference (unet.py:15-51). With drop_rate=0 (every shipped inference path,
+    """Input dropout of the reference (unet.py:15-51): every pixel is kept with probability 1-drop_rate and otherwise
+    replaced by its KB prediction (reflect padding). With drop_rate=0 (every shipped inference path,
     src/unet/evaluate.py:175-181) the keep-probability is 1 and the layer is the identity, so it is elided.
-    drop_rate>0 is a training-time feature and is not implemented."""
+    For drop_rate>0 (training-time feature) the blend runs as plain torch ops on the input's
+    device. Differences from the reference, both deliberate: the caller's tensor is NOT modified in place, and the mask
+    comes from the device RNG (the reference draws it on the CPU), so masks are not reproducible across the two."""
 
     def __init__(self, p: float, drop_channel):
         super().__init__()
         self.p = 1 - p
+        self.kb = torch.tensor([[[[-1, +2, -1], [+2, +0, +2], [-1, +2, -1]]]], dtype=torch.float32) / 4.
         self.drop_channel = drop_channel
+        self.mask = None
 
     def forward(self, x):
-        if self.p != 1:
-            raise NotImplementedError("UniformDropout with drop_rate>0 is training-only and not implemented")
-        return x
+        if self.p == 1:
+            return x
+        c = list(self.drop_channel)
+        xf = x.to(torch.float32) / 255. if x.dtype == torch.uint8 else x
+        self.mask = torch.empty(xf.shape[0], 1, *xf.shape[2:], device=xf.device).bernoulli_(p=self.p).repeat(1, len(c), 1, 1)
+        x_pad = torch.nn.functional.pad(xf[:, c], (1, 1, 1, 1), mode='reflect')
+        x_kb = torch.nn.functional.conv2d(x_pad, self.kb.to(xf.device).repeat(len(c), 1, 1, 1), groups=len(c))
+        out = xf.clone()
+        out[:, c] = xf[:, c] * self.mask + x_kb * (1 - self.mask)
+        return out
 
 
 class UNet(nn.Module):

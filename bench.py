@@ -77,10 +77,10 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-def make_inputs(n, device):
+def make_inputs(n, device, size=512):
     from ws_unet_b200 import data as wdata
     per = (n + len(ALPHAS) - 1) // len(ALPHAS)
-    parts = [wdata.synthetic_stego_fast(per, a, 512, 512, device, seed=i, unique=32) for i, a in enumerate(ALPHAS)]
+    parts = [wdata.synthetic_stego_fast(per, a, size, size, device, seed=i, unique=32 if size <= 512 else 8) for i, a in enumerate(ALPHAS)]
     import torch
     return torch.cat(parts)[:n].contiguous()
 
@@ -167,7 +167,8 @@ def run_ours(args):
     pk = peaks()
     per_gpu = args.per_gpu
     model = build_model(dev)
-    imgs = make_inputs(per_gpu, dev)
+    S = args.size
+    imgs = make_inputs(per_gpu, dev, S)
     if args.micro_batch:
         model.set_micro_batch(args.micro_batch, dev)
     n_total = per_gpu * world
@@ -209,7 +210,7 @@ def run_ours(args):
     host_out = torch.empty(2, per_gpu, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        _native.check(lib.wsu_unet_ws_estimate_host(h, ctypes.c_void_p(host_img.data_ptr()), per_gpu, 512, 512, 0, 1, 1,
+        _native.check(lib.wsu_unet_ws_estimate_host(h, ctypes.c_void_p(host_img.data_ptr()), per_gpu, S, S, 0, 1, 1,
                                                     ctypes.c_void_p(host_out[0].data_ptr()), ctypes.c_void_p(host_out[1].data_ptr())))
 
     for _ in range(max(1, args.warmup // 2)):
@@ -229,6 +230,7 @@ def run_ours(args):
     if rank != 0:
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
         return
 
     # ---- per-layer device times (one extra profiled step, rank 0) -> roofline of the tensor-core chain
@@ -249,10 +251,10 @@ def run_ours(args):
     layers = []
     for i in range(max(0, n_layers)):
         name = lib.wsu_profile_name(h, i).decode()
-        tf = layer_gflop.get(name, 0.0) * last_mb / (buf[i] * 1e-3) / 1e3 if buf[i] > 0 else 0.0
+        tf = layer_gflop.get(name, 0.0) * (S / 512) ** 2 * last_mb / (buf[i] * 1e-3) / 1e3 if buf[i] > 0 else 0.0
         layers.append({'layer': name, 'ms': round(buf[i], 4), 'tflops': round(tf, 1)})
     conv_ms = sum(l['ms'] for l in layers if l['layer'] != 'e11')
-    conv_gflop = sum(layer_gflop[l['layer']] for l in layers if l['layer'] != 'e11')
+    conv_gflop = sum(layer_gflop[l['layer']] for l in layers if l['layer'] != 'e11') * (S / 512) ** 2
     achieved = conv_gflop * last_mb / (conv_ms * 1e-3) / 1e3 if conv_ms else 0.0
 
     # ---- estimator (HBM-bound, BASELINE.json configs[1]): KB-filter WS on resident uint8 images
@@ -271,7 +273,7 @@ def run_ours(args):
         a1.record()
         torch.cuda.synchronize()
         sec = a0.elapsed_time(a1) / reps / 1e3
-        gbs = EST_BYTES_PER_IMG * n_est / sec / 1e9
+        gbs = (S * S + 4) * n_est / sec / 1e9
         est[f'kb_w{weighted}'] = {'images_per_s': n_est / sec, 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                                    'frac': gbs / pk['hbm_gbs'], 'bound': 'hbm', 'images': n_est}
     del est_imgs
@@ -280,19 +282,19 @@ def run_ours(args):
     cpu_v, cpu_n, cores = cpu_baseline_run(seconds=args.cpu_seconds)
 
     line = {
-        'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'metric': METRIC if S == 512 else f'UNet-WS {S}x{S} images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'bf16x3 (split-bf16 operands, 3 tcgen05 MMAs per MAC, fp32 accumulate)', 'data': 'synthetic',
-        'config': {'workload': f'UNet-WS (unet_2 random init) beta_hat on {per_gpu} synthetic 512x512 uint8 LSBr stego images per '
+        'config': {'workload': f'UNet-WS (unet_2 random init) beta_hat on {per_gpu} synthetic {S}x{S} uint8 LSBr stego images per '
                                f'GPU, alpha sweep {ALPHAS}, weighted=0 (BASELINE configs[2]; sharded by image at N>1 = configs[3])',
                    'images_per_step': n_total, 'micro_batch': mb, 'parallelism': f'image-sharded x{world}, all_gather(beta_hat)',
                    'l2_policy': 'working set per micro-batch (>= 8 GB of activations) far exceeds the 126 MB L2; no flush needed'},
         'clocks': clocks,
-        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': per_gpu * 512 * 512 * world,
+        'e2e': {'value': e2e_value, 'unit': 'images/s', 'h2d_bytes_per_step': per_gpu * S * S * world,
                 'd2h_bytes_per_step': per_gpu * 8 * world, 'matches_device_path': e2e_ok},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
-                     'frac': achieved / pk['tf_sustained'], 'traffic': None, 'peak_source': pk['source'] + ' sustained bf16',
+                     'frac': achieved / pk['tf_sustained'], 'traffic': 0.922e9 * last_mb * (S / 512) ** 2, 'traffic_note': 'dram__bytes_read+write summed over the 11 launches of a 32-image pass from the ncu --set full capture in profiles/r01_ncu_halo_kernels.md (0.922 GB per 512x512 image), scaled to this pass', 'peak_source': pk['source'] + ' sustained bf16',
                      'kernel': 'conv_mma_kernel (11 launches per micro-batch)', 'issued_tflops': 3 * achieved,
                      'issued_frac': 3 * achieved / pk['tf_sustained'],
                      'note': 'achieved = algorithmic 2*MACs of the 11 tensor-core layers / their summed CUDA-event time; '
@@ -306,6 +308,7 @@ def run_ours(args):
     print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -319,6 +322,7 @@ def main():
     ap.add_argument('--est-images', type=int, default=10000, help='images of the KB-filter estimator measurement (configs[1])')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--profile-images', type=int, default=32, help='images of the per-layer profiled pass')
+    ap.add_argument('--size', type=int, default=512, help='image side; 1024 = BASELINE configs[4] (not the headline metric)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

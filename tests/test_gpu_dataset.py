@@ -72,15 +72,15 @@ def test_wsloss_wsmeter_match_reference_definitions(cuda_dev, ws_golden):
 
 
 def test_roc_from_gpu_beta_hat(cuda_dev):
-    """N3: the consumer of beta_hat. KB-WS on synthetic covers vs alpha=0.1 stego must separate almost perfectly."""
+    """N3: the consumer of beta_hat. KB-WS on synthetic covers vs alpha=0.4 stego must separate almost perfectly."""
     import ws_unet_b200 as W
     from ws_unet_b200 import data as wdata
     from ws_unet_b200.metrics import produce_roc
-    covers = wdata.synthetic_covers(24, 128, 128)
-    stego = torch.stack([wdata.embed_lsbr(covers[i, 0], 0.1, i) for i in range(24)])[:, None]
+    covers = wdata.synthetic_covers(24, 256, 256)
+    stego = torch.stack([wdata.embed_lsbr(covers[i, 0], 0.4, i) for i in range(24)])[:, None]
     bc = W.ws_estimate(covers.to(cuda_dev), 'KB', weighted=1).cpu().numpy()
     bs = W.ws_estimate(stego.to(cuda_dev), 'KB', weighted=1).cpu().numpy()
-    df = pd.DataFrame({'stego_method': ['Cover'] * 24 + ['LSBR'] * 24, 'model_name': 'KB', 'alpha': [0.] * 24 + [0.1] * 24,
+    df = pd.DataFrame({'stego_method': ['Cover'] * 24 + ['LSBR'] * 24, 'model_name': 'KB', 'alpha': [0.] * 24 + [0.4] * 24,
                        'beta_hat': np.concatenate([bc, bs])})
     roc = produce_roc(df)
     assert roc['auc'].iloc[0] > 0.95 and roc['p_e'].iloc[0] < 0.1

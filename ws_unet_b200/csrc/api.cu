@@ -758,9 +758,12 @@ int wsu_filter_ws_estimate(int device, const void* img_dev, int img_dtype, int k
   float* partials = nullptr;
   int records = filter_ws_strips(H);
   const bool fast = filter_ws_fast_ok(img_dev, img_dtype == WSU_F32, W, kind, correct_bias, nullptr);
-  if (fast) records = filter_ws_fast_records(H, W);
+  const bool packed = fast && weighted == WSU_UNWEIGHTED && l1_dev == nullptr;
+  if (fast) records = packed ? filter_ws_packed_records(H, W) : filter_ws_fast_records(H, W);
   CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partials), size_t(B) * records * kPartialSlots * 4, st));
-  if (fast)
+  if (packed)
+    LAUNCH_TRY(launch_filter_ws_packed(img_dev, B, H, W, kind, partials, st));
+  else if (fast)
     LAUNCH_TRY(launch_filter_ws_fast(img_dev, B, H, W, kind, weighted, partials, st));
   else
     LAUNCH_TRY(launch_filter_ws(img_dev, img_dtype == WSU_F32, B, H, W, kind, weighted, correct_bias, nullptr, partials, st));

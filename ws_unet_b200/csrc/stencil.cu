@@ -389,6 +389,125 @@ __global__ void __launch_bounds__(kFastThreads) filter_ws_fast_kernel(const uint
   }
 }
 
+// ------------------------------------------------------------------------------------------------ packed filter WS
+// Unweighted KB / AVG beta_hat only (no l1): two pixels per 32-bit register in 16-bit lanes, plain integer adds (every
+// intermediate fits: 8-neighbour sums <= 2040, biased residual in [8, 4088]), so one ALU instruction advances two
+// pixels. Per lane the kernel accumulates (x - x_bar) * S*(x - x_hat) + 2048 (S = 4 for KB, 8 for AVG); lanes are
+// flushed into 32-bit sums every 12 rows (12 * 4088 < 65536) and the bias is removed analytically at the end.
+constexpr int kPackRows = 36;  // interior rows per CTA (3 flush groups of 12 = 6 chunks of 6)
+
+__device__ __forceinline__ uint32_t pair_lo(uint32_t w, uint32_t sel) { return __byte_perm(w, 0u, sel); }
+
+template <int KIND>
+__global__ void __launch_bounds__(kFastThreads) filter_ws_packed_kernel(const uint8_t* __restrict__ img, int H, int W,
+                                                                        float* __restrict__ partials, int strips, int xtiles) {
+  const int xt = blockIdx.x % xtiles;
+  const int strip = (blockIdx.x / xtiles) % strips;
+  const int b = blockIdx.x / (xtiles * strips);
+  const int lane = threadIdx.x & 31;
+  const int x = xt * (kFastThreads * 4) + threadIdx.x * 4;
+  const bool active = x < W;
+  const int y0 = 1 + strip * kPackRows;
+  const int yend = min(y0 + kPackRows, H - 1);
+  const uint8_t* base = img + size_t(b) * H * W;
+  const bool need_l = (lane == 0) && active && x > 0;
+  const bool need_r = (lane == 31) && active && (x + 4 < W);
+  // lane masks of the two output pairs (pixels x..x+1 and x+2..x+3): interior columns only
+  auto in_col = [&](int c) { return active && (x + c >= 1) && (x + c <= W - 2); };
+  const uint32_t m12 = (in_col(0) ? 0x0000ffffu : 0u) | (in_col(1) ? 0xffff0000u : 0u);
+  const uint32_t m34 = (in_col(2) ? 0x0000ffffu : 0u) | (in_col(3) ? 0xffff0000u : 0u);
+  const int valid_cols = int(in_col(0)) + int(in_col(1)) + int(in_col(2)) + int(in_col(3));
+
+  // packed pairs of one image row: p[0]=(c0,c1) p[1]=(c1,c2) p[2]=(c2,c3) p[3]=(c3,c4) p[4]=(c4,c5); c1..c4 = own pixels
+  auto fetch = [&](int y, uint32_t& w, uint32_t& le, uint32_t& re) {
+    const uint8_t* row = base + size_t(y) * W;
+    w = active ? __ldg(reinterpret_cast<const uint32_t*>(row + x)) : 0u;
+    le = need_l ? (uint32_t(__ldg(row + x - 1)) << 24) : 0u;
+    re = need_r ? uint32_t(__ldg(row + x + 4)) : 0u;
+  };
+  auto unpack = [&](uint32_t w, uint32_t le, uint32_t re, uint32_t (&p)[5]) {
+    uint32_t lw = __shfl_up_sync(0xffffffffu, w, 1), rw = __shfl_down_sync(0xffffffffu, w, 1);
+    lw = lane == 0 ? le : lw;
+    rw = lane == 31 ? re : rw;
+    const uint32_t wl = __funnelshift_r(lw, w, 24);  // bytes (c0, c1, c2, c3)
+    const uint32_t wr = __funnelshift_r(w, rw, 8);   // bytes (c2, c3, c4, c5)
+    p[0] = pair_lo(wl, 0x4140);
+    p[1] = pair_lo(w, 0x4140);
+    p[2] = pair_lo(w, 0x4241);
+    p[3] = pair_lo(w, 0x4342);
+    p[4] = pair_lo(wr, 0x4342);
+  };
+  uint32_t top[5], mid[5];
+  {
+    uint32_t w0, l0, r0, w1, l1, r1;
+    fetch(y0 - 1, w0, l0, r0);
+    fetch(y0, w1, l1, r1);
+    unpack(w0, l0, r0, top);
+    unpack(w1, l1, r1, mid);
+  }
+  constexpr uint32_t kBias = 0x08000800u, kTwoBias = 0x10001000u;
+  long long total = 0;
+  int rows_done = 0;
+  for (int yg = y0; yg < yend; yg += 12) {
+    uint32_t acc12 = 0, acc34 = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int yc = yg + half * 6;
+      uint32_t w[6], le[6], re[6];
+#pragma unroll
+      for (int r = 0; r < 6; ++r) fetch(min(yc + r + 1, H - 1), w[r], le[r], re[r]);
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        uint32_t bot[5];
+        unpack(w[r], le[r], re[r], bot);
+        if (yc + r < yend) {
+          uint32_t vs[5];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) vs[k] = top[k] + bot[k];
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            // output pair o: centre pair index 1 + 2*o, left-neighbour pair 2*o, right-neighbour pair 2 + 2*o
+            const uint32_t C = mid[1 + 2 * o], sh = mid[2 * o] + mid[2 + 2 * o];
+            uint32_t eb;
+            if (KIND == PRED_KB) {
+              const uint32_t t = vs[1 + 2 * o] + sh;                       // N+S+W+E
+              const uint32_t P = 4u * C + (vs[2 * o] + vs[2 + 2 * o] + kBias);  // 4x + diagonals + bias
+              eb = P - 2u * t;                                             // 4(x - x_hat) + 2048 per lane
+            } else {
+              const uint32_t s8 = vs[2 * o] + vs[1 + 2 * o] + vs[2 + 2 * o] + sh;
+              eb = 8u * C + kBias - s8;                                    // 8(x - x_hat) + 2048 per lane
+            }
+            const uint32_t odd = (C & 0x00010001u) * 0xffffu;              // 0xffff in lanes with odd x
+            const uint32_t deb = (eb & odd) | ((kTwoBias - eb) & ~odd);    // (x - x_bar) * residual + 2048
+            if (o == 0) acc12 += deb & m12; else acc34 += deb & m34;
+          }
+          ++rows_done;
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { top[k] = mid[k]; mid[k] = bot[k]; }
+      }
+    }
+    total += (acc12 & 0xffffu) + (acc12 >> 16) + (acc34 & 0xffffu) + (acc34 >> 16);
+  }
+  total -= 2048ll * rows_done * valid_cols;
+  const int npx = rows_done * valid_cols;
+  // CTA reduction (exact integers; |total| per CTA < 2^31)
+  __shared__ int ired[kFastThreads / 32][2];
+  const int warp = threadIdx.x >> 5;
+  const int r0 = __reduce_add_sync(0xffffffffu, int(total)), r1 = __reduce_add_sync(0xffffffffu, npx);
+  if (lane == 0) { ired[warp][0] = r0; ired[warp][1] = r1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int sr = 0, sn = 0;
+    for (int i = 0; i < kFastThreads / 32; ++i) { sr += ired[i][0]; sn += ired[i][1]; }
+    constexpr float kScale = (KIND == PRED_KB) ? 0.25f : 0.125f;
+    float* dst = partials + (size_t(b) * strips * xtiles + size_t(strip) * xtiles + xt) * 2 * kPartialSlots;
+    const int sr_lo = sr & 0xfff;
+    dst[0] = float(sr - sr_lo) * kScale; dst[1] = float(sn); dst[2] = 0.f; dst[3] = 0.f;
+    dst[4] = float(sr_lo) * kScale;      dst[5] = 0.f;       dst[6] = 0.f; dst[7] = 0.f;
+  }
+}
+
 // WS terms against a caller-supplied prediction (pixel units), grid-stride per image chunk.
 template <bool kFloatIn>
 __global__ void __launch_bounds__(256) ws_from_pred_kernel(const void* __restrict__ img, const float* __restrict__ xhat,
@@ -560,6 +679,19 @@ static void launch_fast_kind(const uint8_t* img, int B, int H, int W, int weight
     filter_ws_fast_kernel<KIND, WS_WEIGHTED><<<grid, kFastThreads, 0, stream>>>(img, H, W, partials, strips, xtiles);
   else
     filter_ws_fast_kernel<KIND, WS_ANTIWEIGHTED><<<grid, kFastThreads, 0, stream>>>(img, H, W, partials, strips, xtiles);
+}
+
+int filter_ws_packed_records(int H, int W) {
+  return ((H - 2 + kPackRows - 1) / kPackRows) * ((W + kFastThreads * 4 - 1) / (kFastThreads * 4)) * 2;
+}
+cudaError_t launch_filter_ws_packed(const void* img, int B, int H, int W, int kind, float* partials, cudaStream_t stream) {
+  const int strips = (H - 2 + kPackRows - 1) / kPackRows;
+  const int xtiles = (W + kFastThreads * 4 - 1) / (kFastThreads * 4);
+  const uint8_t* im = static_cast<const uint8_t*>(img);
+  const int grid = B * strips * xtiles;
+  if (kind == PRED_KB) filter_ws_packed_kernel<PRED_KB><<<grid, kFastThreads, 0, stream>>>(im, H, W, partials, strips, xtiles);
+  else filter_ws_packed_kernel<PRED_AVG><<<grid, kFastThreads, 0, stream>>>(im, H, W, partials, strips, xtiles);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_filter_ws_fast(const void* img, int B, int H, int W, int kind, int weighted, float* partials,

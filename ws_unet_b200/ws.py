@@ -48,7 +48,8 @@ def ws_estimate(images: torch.Tensor, predictor, weighted: int = 0, clip: bool =
     dev = images.device
     lib = _native.load()
     beta = torch.empty(B, dtype=torch.float32, device=dev)
-    l1 = torch.empty(B, dtype=torch.float32, device=dev)
+    l1 = torch.empty(B, dtype=torch.float32, device=dev) if return_l1 else None
+    l1_ptr = ctypes.c_void_p(l1.data_ptr()) if l1 is not None else None
     with torch.cuda.device(dev):
         st = _native.stream_ptr(dev)
         if isinstance(predictor, str):
@@ -58,7 +59,7 @@ def ws_estimate(images: torch.Tensor, predictor, weighted: int = 0, clip: bool =
                 raise ValueError("linear filters are 'valid' convolutions: crop must be 1")
             _native.check(lib.wsu_filter_ws_estimate(
                 dev.index, ctypes.c_void_p(images.data_ptr()), dtype, _native.PRED_KINDS[predictor], int(weighted),
-                int(bool(clip)), int(bool(correct_bias)), ctypes.c_void_p(beta.data_ptr()), ctypes.c_void_p(l1.data_ptr()),
+                int(bool(clip)), int(bool(correct_bias)), ctypes.c_void_p(beta.data_ptr()), l1_ptr,
                 B, H, W, st), 'wsu_filter_ws_estimate')
             pred = filters.filter_predict(images, predictor) if return_prediction else None
         elif isinstance(predictor, UNet):
@@ -67,7 +68,7 @@ def ws_estimate(images: torch.Tensor, predictor, weighted: int = 0, clip: bool =
             if not correct_bias:
                 _native.check(lib.wsu_unet_ws_estimate(
                     h, ctypes.c_void_p(images.data_ptr()), dtype, B, H, W, int(weighted), int(bool(clip)), int(crop),
-                    ctypes.c_void_p(beta.data_ptr()), ctypes.c_void_p(l1.data_ptr()),
+                    ctypes.c_void_p(beta.data_ptr()), l1_ptr,
                     ctypes.c_void_p(yhat.data_ptr()) if yhat is not None else None, st), 'wsu_unet_ws_estimate')
             else:
                 # estimate.py:126-128: second predictor pass on the difference image x_bar - x (values +-1),
@@ -83,7 +84,7 @@ def ws_estimate(images: torch.Tensor, predictor, weighted: int = 0, clip: bool =
                 _native.check(lib.wsu_ws_from_prediction(
                     dev.index, ctypes.c_void_p(images.data_ptr()), dtype, ctypes.c_void_p(xhat.data_ptr()), 0,
                     ctypes.c_void_p(xbias.data_ptr()), int(weighted), int(bool(clip)), int(crop),
-                    ctypes.c_void_p(beta.data_ptr()), ctypes.c_void_p(l1.data_ptr()), B, H, W, st), 'wsu_ws_from_prediction')
+                    ctypes.c_void_p(beta.data_ptr()), l1_ptr, B, H, W, st), 'wsu_ws_from_prediction')
             pred = yhat
         else:
             raise TypeError("predictor must be a ws_unet_b200 UNet or one of " + str(list(_native.PRED_KINDS)))

@@ -410,25 +410,26 @@ __global__ void __launch_bounds__(kFastThreads) filter_ws_packed_kernel(const ui
   const int y0 = 1 + strip * kPackRows;
   const int yend = min(y0 + kPackRows, H - 1);
   const uint8_t* base = img + size_t(b) * H * W;
-  const bool need_l = (lane == 0) && active && x > 0;
-  const bool need_r = (lane == 31) && active && (x + 4 < W);
   // lane masks of the two output pairs (pixels x..x+1 and x+2..x+3): interior columns only
   auto in_col = [&](int c) { return active && (x + c >= 1) && (x + c <= W - 2); };
   const uint32_t m12 = (in_col(0) ? 0x0000ffffu : 0u) | (in_col(1) ? 0xffff0000u : 0u);
   const uint32_t m34 = (in_col(2) ? 0x0000ffffu : 0u) | (in_col(3) ? 0xffff0000u : 0u);
   const int valid_cols = int(in_col(0)) + int(in_col(1)) + int(in_col(2)) + int(in_col(3));
 
-  // packed pairs of one image row: p[0]=(c0,c1) p[1]=(c1,c2) p[2]=(c2,c3) p[3]=(c3,c4) p[4]=(c4,c5); c1..c4 = own pixels
-  auto fetch = [&](int y, uint32_t& w, uint32_t& le, uint32_t& re) {
-    const uint8_t* row = base + size_t(y) * W;
-    w = active ? __ldg(reinterpret_cast<const uint32_t*>(row + x)) : 0u;
-    le = need_l ? (uint32_t(__ldg(row + x - 1)) << 24) : 0u;
-    re = need_r ? uint32_t(__ldg(row + x + 4)) : 0u;
+  // packed pairs of one image row: p[0]=(c0,c1) p[1]=(c1,c2) p[2]=(c2,c3) p[3]=(c3,c4) p[4]=(c4,c5); c1..c4 = own pixels.
+  // Each thread loads its own aligned word and the words left and right of it (immediate offsets from one row pointer,
+  // L1 hits): no shuffles, no warp-edge special cases.
+  const bool has_l = active && x > 0, has_r = active && (x + 4 < W);
+  const uint8_t* rp = base + size_t(y0 - 1) * W + (active ? x : 0);
+  int yrow = y0 - 1;
+  auto fetch = [&](uint32_t& w, uint32_t& lw, uint32_t& rw) {
+    w = active ? __ldg(reinterpret_cast<const uint32_t*>(rp)) : 0u;
+    lw = has_l ? __ldg(reinterpret_cast<const uint32_t*>(rp - 4)) : 0u;
+    rw = has_r ? __ldg(reinterpret_cast<const uint32_t*>(rp + 4)) : 0u;
+    if (yrow < H - 1) rp += W;  // rows past the image bottom re-read the last row (their results are never used)
+    ++yrow;
   };
-  auto unpack = [&](uint32_t w, uint32_t le, uint32_t re, uint32_t (&p)[5]) {
-    uint32_t lw = __shfl_up_sync(0xffffffffu, w, 1), rw = __shfl_down_sync(0xffffffffu, w, 1);
-    lw = lane == 0 ? le : lw;
-    rw = lane == 31 ? re : rw;
+  auto unpack = [&](uint32_t w, uint32_t lw, uint32_t rw, uint32_t (&p)[5]) {
     const uint32_t wl = __funnelshift_r(lw, w, 24);  // bytes (c0, c1, c2, c3)
     const uint32_t wr = __funnelshift_r(w, rw, 8);   // bytes (c2, c3, c4, c5)
     p[0] = pair_lo(wl, 0x4140);
@@ -440,8 +441,8 @@ __global__ void __launch_bounds__(kFastThreads) filter_ws_packed_kernel(const ui
   uint32_t top[5], mid[5];
   {
     uint32_t w0, l0, r0, w1, l1, r1;
-    fetch(y0 - 1, w0, l0, r0);
-    fetch(y0, w1, l1, r1);
+    fetch(w0, l0, r0);
+    fetch(w1, l1, r1);
     unpack(w0, l0, r0, top);
     unpack(w1, l1, r1, mid);
   }
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(kFastThreads) filter_ws_packed_kernel(const ui
       const int yc = yg + half * 6;
       uint32_t w[6], le[6], re[6];
 #pragma unroll
-      for (int r = 0; r < 6; ++r) fetch(min(yc + r + 1, H - 1), w[r], le[r], re[r]);
+      for (int r = 0; r < 6; ++r) fetch(w[r], le[r], re[r]);
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
         uint32_t bot[5];
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(kFastThreads) filter_ws_packed_kernel(const ui
             }
             const uint32_t odd = (C & 0x00010001u) * 0xffffu;              // 0xffff in lanes with odd x
             const uint32_t deb = (eb & odd) | ((kTwoBias - eb) & ~odd);    // (x - x_bar) * residual + 2048
-            if (o == 0) acc12 += deb & m12; else acc34 += deb & m34;
+            if (o == 0) acc12 += deb; else acc34 += deb;   // border lanes are masked when the lanes are flushed
           }
           ++rows_done;
         }
@@ -487,6 +488,8 @@ __global__ void __launch_bounds__(kFastThreads) filter_ws_packed_kernel(const ui
         for (int k = 0; k < 5; ++k) { top[k] = mid[k]; mid[k] = bot[k]; }
       }
     }
+    acc12 &= m12;
+    acc34 &= m34;
     total += (acc12 & 0xffffu) + (acc12 >> 16) + (acc34 & 0xffffu) + (acc34 >> 16);
   }
   total -= 2048ll * rows_done * valid_cols;

@@ -258,3 +258,83 @@ def test_unet_1024_matches_oracle_strip(cuda_dev):
     yb = m(big)
     assert yb.shape == (2, 1, 1024, 1024) and torch.isfinite(yb).all()
     assert torch.equal(yb[:1], m(big[:1]))                        # batch independence at full size
+
+
+# ------------------------------------------------------------------------------------------------ kernel variants and state
+def test_kernel_variants_agree(cuda_dev):
+    """The halo-box / per-tap 3x3 kernels and the resident / per-phase up-convolutions are interchangeable: same
+    predictions within fp32 summation noise, both within tolerance of the oracle."""
+    from ws_unet_b200 import _native
+    sd = uo.numpy_weights(2, seed=17)
+    m = _model(2, 17, cuda_dev)
+    x = np.random.default_rng(8).random((2, 1, 80, 112), dtype=np.float32)
+    xd = torch.from_numpy(x).to(cuda_dev)
+    y_ref = uo.unet_forward(sd, x, 2)
+    lib, h = _native.load(), m.native_handle(cuda_dev)
+    outs = {}
+    for halo in (1, 0):
+        for res in (1, 0):
+            _native.check(lib.wsu_set_option(h, b'halo', halo))
+            _native.check(lib.wsu_set_option(h, b'upconv_resident', res))
+            outs[(halo, res)] = m(xd).cpu().numpy()
+            assert np.abs(outs[(halo, res)] - y_ref).max() * 255 < PX_TOL, (halo, res)
+    lib.wsu_set_option(h, b'halo', 1)
+    lib.wsu_set_option(h, b'upconv_resident', 1)
+    assert np.abs(outs[(1, 1)] - outs[(0, 0)]).max() * 255 < 1e-4
+    with pytest.raises(ValueError):
+        _native.check(lib.wsu_set_option(h, b'no_such_option', 1))
+
+
+def test_weight_updates_are_picked_up(cuda_dev):
+    """load_state_dict / in-place edits (disable_center_pixels, unet.py:196-199) must reach the packed device weights."""
+    m = _model(2, 3, cuda_dev)
+    x = torch.rand(1, 1, 32, 32, device=cuda_dev)
+    y0 = m(x)
+    m.disable_center_pixels()
+    y1 = m(x)
+    assert not torch.equal(y0, y1)
+    sd = uo.numpy_weights(2, seed=3)
+    sd['e11.weight'][:, :, 1, 1] = 0
+    y_ref = uo.unet_forward(sd, x.cpu().numpy(), 2)
+    assert np.abs(y1.cpu().numpy() - y_ref).max() * 255 < PX_TOL
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in uo.numpy_weights(2, seed=4).items()})
+    y2 = m(x)
+    assert np.abs(y2.cpu().numpy() - uo.unet_forward(uo.numpy_weights(2, seed=4), x.cpu().numpy(), 2)).max() * 255 < PX_TOL
+
+
+def test_shape_changes_and_streams(cuda_dev):
+    """Plans are rebuilt when the image size changes; calls on a non-default stream are ordered on that stream."""
+    import ws_unet_b200 as W
+    sd = uo.numpy_weights(1, seed=6)
+    m = _model(1, 6, cuda_dev)
+    for hw in [(32, 32), (64, 48), (32, 32), (16, 128)]:
+        x = np.random.default_rng(hw[0] + hw[1]).random((3, 1) + hw, dtype=np.float32)
+        y = m(torch.from_numpy(x).to(cuda_dev)).cpu().numpy()
+        assert np.abs(y - uo.unet_forward(sd, x, 1)).max() * 255 < PX_TOL
+    s = torch.cuda.Stream(device=cuda_dev)
+    img = torch.randint(0, 256, (4, 1, 64, 64), dtype=torch.uint8, device=cuda_dev)
+    ref = W.ws_estimate(img, m, weighted=0, clip=False)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        got = W.ws_estimate(img, m, weighted=0, clip=False)
+        kb = W.ws_estimate(img, 'KB')
+    s.synchronize()
+    assert torch.equal(got, ref) and torch.equal(kb, W.ws_estimate(img, 'KB'))
+
+
+def test_uniform_dropout_blend(cuda_dev):
+    """drop_rate > 0 (unet.py:15-51): dropped pixels are replaced by their KB prediction; the caller's tensor is untouched."""
+    import ws_unet_b200 as W
+    m = W.get_model('unet_1', 1, drop_rate=0.5).to(cuda_dev)
+    x = torch.rand(2, 1, 32, 32, device=cuda_dev)
+    x0 = x.clone()
+    torch.manual_seed(0)
+    y = m(x)
+    assert torch.equal(x, x0) and y.shape == (2, 1, 32, 32)
+    mask = m.input_dropout.mask
+    assert 0.3 < mask.mean().item() < 0.7
+    kb = torch.tensor([[-1, 2, -1], [2, 0, 2], [-1, 2, -1]], dtype=torch.float32, device=cuda_dev)[None, None] / 4
+    x_kb = torch.nn.functional.conv2d(torch.nn.functional.pad(x, (1, 1, 1, 1), mode='reflect'), kb)
+    blended = x * mask + x_kb * (1 - mask)
+    m.input_dropout.p = 1  # identity from here on: forward(blended) must reproduce y
+    assert torch.equal(m(blended), y)

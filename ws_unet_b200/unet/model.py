@@ -177,6 +177,12 @@ class UNet(nn.Module):
         self.e11.weight.data[:, :, 1, 1] = 0.
         if self.e11.weight.grad is not None:
             self.e11.weight.grad[:, :, 1, 1] = 0.
+        self.refresh_weights()
+
+    def refresh_weights(self):
+        """Force a re-pack of the device weights on the next forward. Needed only after edits through `.data`
+        (which do not bump tensor version counters); load_state_dict, optimizer steps and .to() are detected."""
+        self._weights_key = None
 
     def set_micro_batch(self, n: int, device=None):
         """Images per pass through the layer chain (0 = auto from free HBM budget)."""

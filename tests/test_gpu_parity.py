@@ -272,15 +272,18 @@ def test_kernel_variants_agree(cuda_dev):
     y_ref = uo.unet_forward(sd, x, 2)
     lib, h = _native.load(), m.native_handle(cuda_dev)
     outs = {}
-    for halo in (1, 0):
+    for halo, pair in ((1, 0), (1, 1), (1, 2), (0, 0)):
         for res in (1, 0):
             _native.check(lib.wsu_set_option(h, b'halo', halo))
+            _native.check(lib.wsu_set_option(h, b'cta_pair', pair))
             _native.check(lib.wsu_set_option(h, b'upconv_resident', res))
-            outs[(halo, res)] = m(xd).cpu().numpy()
-            assert np.abs(outs[(halo, res)] - y_ref).max() * 255 < PX_TOL, (halo, res)
+            outs[(halo, pair, res)] = m(xd).cpu().numpy()
+            assert np.abs(outs[(halo, pair, res)] - y_ref).max() * 255 < PX_TOL, (halo, pair, res)
     lib.wsu_set_option(h, b'halo', 1)
+    lib.wsu_set_option(h, b'cta_pair', 1)
     lib.wsu_set_option(h, b'upconv_resident', 1)
-    assert np.abs(outs[(1, 1)] - outs[(0, 0)]).max() * 255 < 1e-4
+    assert np.abs(outs[(1, 1, 1)] - outs[(0, 0, 0)]).max() * 255 < 1e-4
+    assert np.array_equal(outs[(1, 2, 1)], outs[(1, 0, 1)])   # CTA pairs issue the same MMAs: bit-identical
     with pytest.raises(ValueError):
         _native.check(lib.wsu_set_option(h, b'no_such_option', 1))
 

@@ -40,12 +40,20 @@ def main():
     h = model.native_handle(dev)
     model.set_micro_batch(n, dev)
     res = {}
+    variant = sys.argv[3] if len(sys.argv) > 3 else 'halo'   # what the left column runs: 'halo' or 'pair'
     for halo in (1, 0):
-        lib.wsu_set_option(h, b'halo', halo)
-        lib.wsu_set_option(h, b'upconv_resident', halo)
-        beta = W.ws_estimate(imgs, model)
-        res[halo] = (profile(model, imgs, lib, h, reps), beta)
-    print('beta halo==per-tap bit-equal:', torch.equal(res[1][1], res[0][1]), ' max|d| =', (res[1][1] - res[0][1]).abs().max().item())
+        if variant == 'pair':
+            lib.wsu_set_option(h, b'halo', 1)
+            lib.wsu_set_option(h, b'cta_pair', halo)
+        else:
+            lib.wsu_set_option(h, b'halo', halo)
+            lib.wsu_set_option(h, b'upconv_resident', halo)
+        beta, yhat = W.ws_estimate(imgs[:8], model, return_prediction=True)
+        torch.cuda.synchronize()
+        res[halo] = (profile(model, imgs, lib, h, reps), beta, yhat)
+    print(f'left column = {variant}, right column = ' + ('halo (single CTA)' if variant == 'pair' else 'per-tap'))
+    print('beta bit-equal:', torch.equal(res[1][1], res[0][1]), ' max|d beta| =', (res[1][1] - res[0][1]).abs().max().item(),
+          ' max|d yhat| px =', ((res[1][2] - res[0][2]).abs().max() * 255).item())
     names = res[1][0][0]
     print(f'{"layer":8s} {"halo ms":>9s} {"TF/s alg":>9s} {"issued":>8s} | {"tap ms":>9s} {"TF/s alg":>9s} {"issued":>8s}   ({n} images)')
     tot = [0.0, 0.0]

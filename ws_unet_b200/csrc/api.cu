@@ -141,6 +141,7 @@ struct wsu_context {
   std::vector<std::string> prof_names;
   int prof_n = 0;
   int last_nimg = 0;  // images in the last micro-batch that ran
+  int use_pair = 1;  // 3x3 layers as CTA pairs (tcgen05 cta_group::2): 0 never, 1 Cout>=128 layers (measured win), 2 all
   bool use_upres = true;  // transposed convs through upconv_res_kernel (option "upconv_resident")
   bool use_halo = true;  // 3x3 layers through conv_halo_kernel (option "halo"; 0 = per-tap reload kernel, for A/B runs)
 };
@@ -395,6 +396,9 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
       UpconvParams u = pl.ups[pl.up_idx[i]];
       if (nimg != pl.mb) { u.B = nimg; u.total_boxes = nimg * u.tiles_x * u.tiles_y; }
       LAUNCH_TRY(launch_upconv_res(u, 4 * u.co_t, h->num_sms, st));
+    } else if (halo && (h->use_pair == 2 || (h->use_pair == 1 && n_tile == 128))) {
+      p.total_items = ((p.total_sub + 3) / 4) * p.n_tiles;   // pair items: 2 slots x 2 CTAs = 4 boxes
+      LAUNCH_TRY(launch_conv_halo2(p, n_tile, epi, h->num_sms, st));
     } else if (halo)
       LAUNCH_TRY(launch_conv_halo(p, n_tile, epi, h->num_sms, st));
     else
@@ -513,6 +517,10 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
   if (!std::strcmp(key, "micro_batch")) {
     if (value < 0) return fail(WSU_ERR_INVALID, "micro_batch must be >= 0");
     h->micro_batch = value;
+    return WSU_OK;
+  }
+  if (!std::strcmp(key, "cta_pair")) {
+    h->use_pair = int(value);
     return WSU_OK;
   }
   if (!std::strcmp(key, "upconv_resident")) {

@@ -649,6 +649,265 @@ cudaError_t launch_halo_t(const ConvParams& p, int num_sms, cudaStream_t stream)
 }
 
 
+// ================================================================================================ CTA-pair halo kernel
+// Same algorithm as conv_halo_kernel, issued as tcgen05.mma.cta_group::2: a cluster of two CTAs computes M = 256
+// (each CTA its own 8x16 pixel box, accumulators in its own TMEM) and each CTA stages only HALF of the B rows, so the
+// shared-memory operand traffic per SM drops from 14/24 KB to 11/18 KB per K=16 step (Cout=64 stacked / Cout>=128) and
+// the weight ring shrinks. Leader CTA (rank 0) issues all MMAs; activation boxes are loaded by each CTA with the
+// cta_group::2 TMA form that credits the leader's mbarrier; weight half-tiles arrive on a local barrier and the idle
+// MMA warp of the peer CTA relays their completion to the leader.
+template <int N_TILE>
+struct H2Cfg {
+  static constexpr bool STACKED = (N_TILE == 64);
+  static constexpr int M_SUB = 2;                 // box slots per item (x 2 CTAs = 4 boxes share one weight pass)
+  static constexpr int ACC_W = 128;
+  static constexpr int SA = 3;
+  static constexpr int W_SLOT = 16384;            // [X tile 8 KB][Y tile 4 KB (stacked) | Z tile 8 KB]
+  static constexpr int W_BYTES = STACKED ? 12288 : 16384;
+  static constexpr int SW = 4;
+  static constexpr int BIAS_BYTES = (N_TILE == 64) ? 256 : 4096;
+  static constexpr int SMEM = SA * kHaloABytes + SW * W_SLOT + kScratchBytes + 1024 + BIAS_BYTES + 256;
+};
+
+template <int N_TILE, int EPI>
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __grid_constant__ ConvParams p) {
+  using C = H2Cfg<N_TILE>;
+  constexpr int M_SUB = C::M_SUB;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + C::SA * kHaloABytes;
+  uint8_t* sScratch = sW + C::SW * C::W_SLOT;
+  float* sBias = reinterpret_cast<float*>(sScratch + kScratchBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + C::BIAS_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + C::SA;
+  uint64_t* w_full = a_empty + C::SA;
+  uint64_t* w_empty = w_full + C::SW;
+  uint64_t* acc_full = w_empty + C::SW;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int items = p.total_items;   // pair items: ceil(total_sub / 4) * n_tiles (host fills this for the pair kernel)
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmapH0);
+    prefetch_tmap(&p.tmapH1);
+    for (int i = 0; i < C::SA; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::SW; ++i) { mbar_init(&w_full[i], leader ? 2 : 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+  for (int i = threadIdx.x; i < p.cout && i < C::BIAS_BYTES / 4; i += kHaloThreads) sBias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / peer-credited TMA
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================== activation boxes: this CTA's box of every slot
+    if (elect_one()) {
+      int as = 0;
+      uint32_t aph = 0;
+      for (int item = pair; item < items; item += npairs) {
+        const int s0 = (item / p.n_tiles) * (2 * M_SUB);
+        const int nslot = min(M_SUB, (p.total_sub - s0 + 1) / 2);
+        for (int c = 0; c < p.cblocks; ++c) {
+          const bool src0 = c < p.cblocks0;
+          const CUtensorMap* tm = src0 ? &p.tmapH0 : &p.tmapH1;
+          const int ch = (src0 ? c : c - p.cblocks0) * 64;
+          for (int j = 0; j < nslot; ++j) {
+            const BoxCoord bc = decode_box(p, min(s0 + 2 * j + int(rank), p.total_sub - 1));
+            mbar_wait(&a_empty[as], aph ^ 1);
+            const uint32_t full_leader = mapa_u32(smem_u32(&a_full[as]), 0);
+            if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kHaloABytes);
+            else mbar_arrive_cluster(full_leader);
+            tma_load_5d_2sm(sA + as * kHaloABytes, tm, full_leader, ch, bc.x0, bc.y0, bc.b, 0);
+            if (++as == C::SA) { as = 0; aph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================================================== weight half-tiles of this CTA
+    if (elect_one()) {
+      int ws = 0;
+      uint32_t wph = 0;
+      const int chunks = p.cblocks * 9;
+      const uint32_t plane_bytes = N_TILE * 128;   // one (hi or lo) tile of the packed chunk
+      for (int item = pair; item < items; item += npairs) {
+        const int nt = item % p.n_tiles;
+        const uint8_t* wsrc = p.wpack + size_t(nt) * chunks * 2 * plane_bytes;
+        for (int q = 0; q < chunks; ++q) {
+          const uint8_t* hi = wsrc + size_t(q) * 2 * plane_bytes;
+          const uint8_t* lo = hi + plane_bytes;
+          uint8_t* dst = sW + ws * C::W_SLOT;
+          mbar_wait(&w_empty[ws], wph ^ 1);
+          mbar_arrive_expect_tx(&w_full[ws], C::W_BYTES);
+          if constexpr (C::STACKED) {
+            bulk_load(dst, rank == 0 ? hi : lo, 8192, &w_full[ws]);                 // X: rows of [Whi; Wlo] owned by this CTA
+            bulk_load(dst + 8192, hi + rank * 4096, 4096, &w_full[ws]);            // Y: this CTA's half of Whi
+          } else {
+            bulk_load(dst, hi + rank * 8192, 8192, &w_full[ws]);                    // X: this CTA's 64 rows of Whi
+            bulk_load(dst + 8192, lo + rank * 8192, 8192, &w_full[ws]);             // Z: this CTA's 64 rows of Wlo
+          }
+          if (++ws == C::SW) { ws = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      if (!leader) {
+        // ===================================================== peer: relay weight arrivals to the leader's barrier
+        int ws = 0;
+        uint32_t wph = 0;
+        for (int item = pair; item < items; item += npairs) {
+          for (int q = 0; q < p.cblocks * 9; ++q) {
+            mbar_wait(&w_full[ws], wph);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&w_full[ws]), 0));
+            if (++ws == C::SW) { ws = 0; wph ^= 1; }
+          }
+        }
+      } else {
+        // ===================================================== leader: MMA issuer for the pair
+        constexpr uint32_t idesc = make_idesc_bf16_m(256, N_TILE);
+        int as = 0, ws = 0, acs = 0;
+        uint32_t aph = 0, wph = 0, acph = 0;
+        for (int item = pair; item < items; item += npairs) {
+          const int s0 = (item / p.n_tiles) * (2 * M_SUB);
+          const int nslot = min(M_SUB, (p.total_sub - s0 + 1) / 2);
+          mbar_wait(&acc_empty[acs], acph ^ 1);
+          tc_fence_after();
+          for (int c = 0; c < p.cblocks; ++c) {
+            uint32_t a_slot[M_SUB];
+            for (int tap = 0; tap < 9; ++tap) {
+              const int wsl = ws;
+              mbar_wait(&w_full[ws], wph);
+              if (++ws == C::SW) { ws = 0; wph ^= 1; }
+              const uint32_t w_x = smem_u32(sW + wsl * C::W_SLOT), w_y = w_x + 8192;
+              const uint32_t tap_off = uint32_t((tap / 3) * (kHaloTW + 2) + (tap % 3)) * 128;
+#pragma unroll
+              for (int j = 0; j < M_SUB; ++j) {
+                if (j < nslot) {
+                  if (tap == 0) {
+                    mbar_wait(&a_full[as], aph);
+                    a_slot[j] = uint32_t(as);
+                    if (++as == C::SA) { as = 0; aph ^= 1; }
+                  }
+                  tc_fence_after();
+                  const uint32_t a_hi = smem_u32(sA + a_slot[j] * kHaloABytes) + tap_off;
+                  const uint32_t a_lo = a_hi + kHaloRows * 128;
+                  const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    const uint64_t da_hi = make_sw128_desc(a_hi + k * 32, kHaloSBO);
+                    const uint64_t da_lo = make_sw128_desc(a_lo + k * 32, kHaloSBO);
+                    const uint64_t dw_x = make_sw128_desc(w_x + k * 32);
+                    const uint64_t dw_y = make_sw128_desc(w_y + k * 32);
+                    if constexpr (C::STACKED) {
+                      umma_bf16_2sm(d, da_hi, dw_x, make_idesc_bf16_m(256, 128), (c | tap | k) != 0);  // Ahi * [Whi; Wlo]
+                      umma_bf16_2sm(d, da_lo, dw_y, make_idesc_bf16_m(256, 64), 1);                    // Alo * Whi
+                    } else {
+                      umma_bf16_2sm(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
+                      umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
+                      umma_bf16_2sm(d, da_hi, dw_y, idesc, 1);
+                    }
+                  }
+                  if (tap == 8) umma_commit_2sm(&a_empty[a_slot[j]], 3);
+                }
+              }
+              umma_commit_2sm(&w_empty[wsl], 3);
+            }
+          }
+          umma_commit_2sm(&acc_full[acs], 3);
+          if (++acs == 2) { acs = 0; acph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (each CTA finishes its own boxes)
+    const int quad = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int ty = row / kHaloTW, tx = row % kHaloTW;
+    int acs = 0;
+    uint32_t acph = 0;
+    for (int item = pair; item < items; item += npairs) {
+      const int nt = item % p.n_tiles;
+      const int s0 = (item / p.n_tiles) * (2 * M_SUB);
+      const int nslot = min(M_SUB, (p.total_sub - s0 + 1) / 2);
+      mbar_wait(&acc_full[acs], acph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = grp; j < nslot; j += 2) {
+        const int s = s0 + 2 * j + int(rank);
+        if (s < p.total_sub) {
+          const BoxCoord bc = decode_box(p, s);
+          const int y = bc.y0 + ty, x = bc.x0 + tx;
+          const bool valid = (y < p.H) && (x < p.W);
+          const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acs * kAccCols + j * C::ACC_W);
+          WsAcc acc;
+          const BoxGeo geo{bc.b, bc.y0, bc.x0, 3, p.H, p.W, 0, 0};
+          epilogue_box<N_TILE, EPI, C::STACKED>(p, sBias, tbase, bc.b, y, x, valid, nt, 0, tx, ty, kHaloTW, acc, geo,
+                                                sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32);
+          if constexpr (EPI == EPI_HEAD) {
+            if (p.partials) {
+              const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1);
+              if (lane == 0) {
+                const size_t subs_per_img = size_t(p.sub_x) * p.sub_y;
+                float* dst = p.partials + ((size_t(bc.b) * subs_per_img + bc.sub_in_img) * 4 + quad) * kPartialSlots;
+                dst[0] = wr;
+                dst[1] = w;
+                dst[2] = l1;
+                dst[3] = 0.f;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[acs]), 0));
+      if (++acs == 2) { acs = 0; acph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be reading this CTA's shared memory / signalling its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+template <int N_TILE, int EPI>
+cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
+  int pairs = num_sms / 2;
+  if (pairs > p.total_items) pairs = p.total_items;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kHaloThreads);
+  cfg.dynamicSmemBytes = H2Cfg<N_TILE>::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<N_TILE, EPI>, p);
+}
+
 // ================================================================================================ resident-weight upconv
 // ConvTranspose2d(k=2, s=2) (unet.py:177,183): out[2y+dy][2x+dx][co] = b[co] + sum_ci in[y][x][ci] * w[ci][co][dy][dx].
 // The four phases are stacked along N and the whole (hi, lo) weight set of the CTA's N tile (128 KB) stays in shared
@@ -804,6 +1063,12 @@ cudaError_t conv_mma_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<64>::SMEM);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upconv_res_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upconv_res_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
@@ -848,5 +1113,19 @@ cudaError_t launch_upconv_res(const UpconvParams& p, int n_tile, int num_sms, cu
   else if (n_tile == 128) upconv_res_kernel<128><<<grid, kUpThreads, kUpSmem, stream>>>(p);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
+}
+}  // namespace wsu
+
+namespace wsu {
+// CTA-pair variant: p.total_items must be ceil(total_sub / 4) * n_tiles
+cudaError_t launch_conv_halo2(const ConvParams& p, int n_tile, int epi, int num_sms, cudaStream_t stream) {
+  if (p.ntaps != 9 || p.npos != 1 || p.upsample) return cudaErrorInvalidValue;
+  if (epi == EPI_HEAD) {
+    if (n_tile != 64 || p.n_tiles != 1) return cudaErrorInvalidValue;
+    return launch_halo2_t<64, EPI_HEAD>(p, num_sms, stream);
+  }
+  if (n_tile == 64) return p.n_tiles == 1 ? launch_halo2_t<64, EPI_ACT>(p, num_sms, stream) : cudaErrorInvalidValue;
+  if (n_tile == 128) return launch_halo2_t<128, EPI_ACT>(p, num_sms, stream);
+  return cudaErrorInvalidValue;
 }
 }  // namespace wsu

@@ -55,6 +55,7 @@ constexpr int wchunk_bytes(int n_tile) { return n_tile * 64 * 2 * 2; }
 cudaError_t launch_conv_mma(const ConvParams& p, int n_tile, int epi, int num_sms, cudaStream_t stream);
 // 3x3 convolutions only: one haloed TMA box per (box, channel block) feeds all 9 taps
 cudaError_t launch_conv_halo(const ConvParams& p, int n_tile, int epi, int num_sms, cudaStream_t stream);
+cudaError_t launch_conv_halo2(const ConvParams& p, int n_tile, int epi, int num_sms, cudaStream_t stream);  // CTA pairs
 constexpr int halo_msub(int) { return 2; }
 constexpr int kHaloTW = 8, kHaloTH = 16;
 // Transposed convolution with shared-memory-resident weights: all 4 output phases stacked along N (N_TILE = 4 * co_t).

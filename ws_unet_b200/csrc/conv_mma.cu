@@ -147,91 +147,91 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&f)[32]) {
 
 template <int N_TILE, int EPI, bool STACKED = false>
 __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* sBias, uint32_t tbase, int b, int y, int x,
-                                             bool valid, int nt, int pos, int tx, int ty, int pool_xor, WsAcc& acc,
-                                             const BoxGeo& geo, uint8_t* scratch, int lane, int row0) {
-        if constexpr (EPI == EPI_ACT) {
+                                       bool valid, int nt, int pos, int tx, int ty, int pool_xor, WsAcc& acc,
+                                       const BoxGeo& geo, uint8_t* scratch, int lane, int row0) {
+  if constexpr (EPI == EPI_ACT) {
 #pragma unroll 1
-          for (int cc = 0; cc < N_TILE / 32; ++cc) {
-            const int n0 = nt * N_TILE + cc * 32;
-            float f[32];
-            load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f);
+    for (int cc = 0; cc < N_TILE / 32; ++cc) {
+      const int n0 = nt * N_TILE + cc * 32;
+      float f[32];
+      load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              f[i] += sBias[n0 + i];
-              if (p.relu) f[i] = fmaxf(f[i], 0.f);
-            }
-            uint32_t h[16], l[16];
+      for (int i = 0; i < 32; ++i) {
+        f[i] += sBias[n0 + i];
+        if (p.relu) f[i] = fmaxf(f[i], 0.f);
+      }
+      uint32_t h[16], l[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
-            store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo);
-            if (p.do_pool) {
-              // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16)
+      for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
+      store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo);
+      if (p.do_pool) {
+        // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16)
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
-                f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], pool_xor));
-              }
-              if (valid && !(tx & 1) && !(ty & 1)) {
+        for (int i = 0; i < 32; ++i) {
+          f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
+          f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], pool_xor));
+        }
+        if (valid && !(tx & 1) && !(ty & 1)) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
-                store_pixel32(p.pool, b, y >> 1, x >> 1, n0, h, l);
-              }
-            }
-          }
-        } else {
-          // 1x1 outconv over the 64 ReLU'd channels of d42, sigmoid, WS residual terms
-          float z = p.bout;
-#pragma unroll 1
-          for (int cc = 0; cc < N_TILE / 32; ++cc) {
-            float f[32];
-            load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float a = fmaxf(f[i] + sBias[cc * 32 + i], 0.f);
-              z = fmaf(a, p.wout[cc * 32 + i], z);
-            }
-          }
-          if (valid) {
-            const float s = 1.f / (1.f + expf(-z));
-            const size_t pix = (size_t(b) * p.H + y) * p.W + x;
-            if (p.yhat) p.yhat[pix] = s;
-            const bool inside = p.crop ? (y >= 1 && y < p.H - 1 && x >= 1 && x < p.W - 1) : true;
-            if (p.img && inside) {
-              const float xhat = s * 255.f;
-              float xv, xbar, s1 = 0.f, s2 = 0.f;
-              if (p.img_is_float) {
-                const float* im = static_cast<const float*>(p.img);
-                ws_load_f32(im[pix], xv, xbar);
-                if (p.weighted != WS_UNWEIGHTED) {
-                  for (int dy = -1; dy <= 1; ++dy)
-                    for (int dx = -1; dx <= 1; ++dx) {
-                      if (dy == 0 && dx == 0) continue;
-                      const float q = im[pix + dy * p.W + dx] * 255.f;
-                      s1 += q;
-                      s2 = fmaf(q, q, s2);
-                    }
-                }
-              } else {
-                const uint8_t* im = static_cast<const uint8_t*>(p.img);
-                ws_load_u8(im[pix], xv, xbar);
-                if (p.weighted != WS_UNWEIGHTED) {
-                  int i1 = 0, i2 = 0;
-                  for (int dy = -1; dy <= 1; ++dy)
-                    for (int dx = -1; dx <= 1; ++dx) {
-                      if (dy == 0 && dx == 0) continue;
-                      const int q = im[pix + dy * p.W + dx];
-                      i1 += q;
-                      i2 += q * q;
-                    }
-                  s1 = float(i1);
-                  s2 = float(i2);
-                }
-              }
-              ws_accumulate(acc, xv, xbar, xhat, ws_weight(p.weighted, s1, s2));
-            }
-          }
+          for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
+          store_pixel32(p.pool, b, y >> 1, x >> 1, n0, h, l);
         }
       }
+    }
+  } else {
+    // 1x1 outconv over the 64 ReLU'd channels of d42, sigmoid, WS residual terms
+    float z = p.bout;
+#pragma unroll 1
+    for (int cc = 0; cc < N_TILE / 32; ++cc) {
+      float f[32];
+      load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float a = fmaxf(f[i] + sBias[cc * 32 + i], 0.f);
+        z = fmaf(a, p.wout[cc * 32 + i], z);
+      }
+    }
+    if (valid) {
+      const float s = 1.f / (1.f + expf(-z));
+      const size_t pix = (size_t(b) * p.H + y) * p.W + x;
+      if (p.yhat) p.yhat[pix] = s;
+      const bool inside = p.crop ? (y >= 1 && y < p.H - 1 && x >= 1 && x < p.W - 1) : true;
+      if (p.img && inside) {
+        const float xhat = s * 255.f;
+        float xv, xbar, s1 = 0.f, s2 = 0.f;
+        if (p.img_is_float) {
+          const float* im = static_cast<const float*>(p.img);
+          ws_load_f32(im[pix], xv, xbar);
+          if (p.weighted != WS_UNWEIGHTED) {
+            for (int dy = -1; dy <= 1; ++dy)
+              for (int dx = -1; dx <= 1; ++dx) {
+                if (dy == 0 && dx == 0) continue;
+                const float q = im[pix + dy * p.W + dx] * 255.f;
+                s1 += q;
+                s2 = fmaf(q, q, s2);
+              }
+          }
+        } else {
+          const uint8_t* im = static_cast<const uint8_t*>(p.img);
+          ws_load_u8(im[pix], xv, xbar);
+          if (p.weighted != WS_UNWEIGHTED) {
+            int i1 = 0, i2 = 0;
+            for (int dy = -1; dy <= 1; ++dy)
+              for (int dx = -1; dx <= 1; ++dx) {
+                if (dy == 0 && dx == 0) continue;
+                const int q = im[pix + dy * p.W + dx];
+                i1 += q;
+                i2 += q * q;
+              }
+            s1 = float(i1);
+            s2 = float(i2);
+          }
+        }
+        ws_accumulate(acc, xv, xbar, xhat, ws_weight(p.weighted, s1, s2));
+      }
+    }
+  }
+}
 
 template <int N_TILE, int EPI>
 __global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_constant__ ConvParams p) {

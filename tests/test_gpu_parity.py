@@ -341,3 +341,26 @@ def test_uniform_dropout_blend(cuda_dev):
     blended = x * mask + x_kb * (1 - mask)
     m.input_dropout.p = 1  # identity from here on: forward(blended) must reproduce y
     assert torch.equal(m(blended), y)
+
+
+def test_host_buffer_entry_points(cuda_dev):
+    """wsu_*_estimate_host (what bench.py times as e2e): pageable and pinned host images, ragged batch vs micro-batch,
+    must equal the device-resident path bit for bit."""
+    import ws_unet_b200 as W
+    from ws_unet_b200 import data as wdata
+    imgs = torch.stack([wdata.embed_lsbr(wdata.synthetic_cover(i, 64, 96), 0.2, i) for i in range(7)])[:, None]
+    m = _model(2, 41, cuda_dev)
+    m.set_micro_batch(3, cuda_dev)                                 # 7 = 3 + 3 + 1
+    ref_b, ref_l = W.ws_estimate(imgs.to(cuda_dev), m, weighted=1, clip=True, return_l1=True)
+    for host in (imgs, imgs.pin_memory()):
+        b, l = W.ws_estimate_host(host, m, weighted=1, clip=True, return_l1=True)
+        assert torch.equal(b, ref_b.cpu()) and torch.equal(l, ref_l.cpu())
+    m.set_micro_batch(0, cuda_dev)
+    for name in ('KB', 'AVG9'):
+        for weighted in (0, 1):
+            ref = W.ws_estimate(imgs.to(cuda_dev), name, weighted=weighted, return_l1=True)
+            got = W.ws_estimate_host(imgs, name, weighted=weighted, return_l1=True)
+            assert torch.equal(got[0], ref[0].cpu()) and torch.equal(got[1], ref[1].cpu())
+            assert torch.equal(W.ws_estimate_host(imgs, name, weighted=weighted), W.ws_estimate(imgs.to(cuda_dev), name, weighted=weighted).cpu())
+    with pytest.raises(ValueError):
+        W.ws_estimate_host(imgs.to(cuda_dev), 'KB')

@@ -3,6 +3,8 @@ uibk-uncover/ws-unet behind the reference's own predictor / estimator interfaces
 from . import _native  # noqa: F401
 from . import filters, unet, ws  # noqa: F401
 from .unet import get_model, UNet  # noqa: F401
-from .ws import ws_estimate, ws_from_prediction, attack  # noqa: F401
+from .ws import ws_estimate, ws_estimate_host, ws_from_prediction, attack  # noqa: F401
+from . import dataset, metrics, parallel  # noqa: F401
 
-__all__ = ['filters', 'unet', 'ws', 'get_model', 'UNet', 'ws_estimate', 'ws_from_prediction', 'attack']
+__all__ = ['filters', 'unet', 'ws', 'dataset', 'metrics', 'parallel', 'get_model', 'UNet', 'ws_estimate', 'ws_estimate_host',
+           'ws_from_prediction', 'attack']

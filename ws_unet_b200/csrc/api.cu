@@ -802,7 +802,7 @@ int wsu_filter_ws_estimate_host(int device, const uint8_t* img_host, int kind, i
     cudaError_t e = cudaMemcpyAsync(dimg + size_t(b0) * px, img_host + size_t(b0) * px, size_t(n) * px, cudaMemcpyHostToDevice, s[k]);
     if (e != cudaSuccess) { rc = fail(WSU_ERR_CUDA, cudaGetErrorString(e)); break; }
     rc = wsu_filter_ws_estimate(device, dimg + size_t(b0) * px, WSU_U8, kind, weighted, clip, correct_bias, dout + b0,
-                                dout + B + b0, n, H, W, s[k]);
+                                l1_host ? dout + B + b0 : nullptr, n, H, W, s[k]);
     if (rc) break;
     cudaMemcpyAsync(beta_host + b0, dout + b0, size_t(n) * 4, cudaMemcpyDeviceToHost, s[k]);
     if (l1_host) cudaMemcpyAsync(l1_host + b0, dout + B + b0, size_t(n) * 4, cudaMemcpyDeviceToHost, s[k]);

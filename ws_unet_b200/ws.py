@@ -96,6 +96,41 @@ def ws_estimate(images: torch.Tensor, predictor, weighted: int = 0, clip: bool =
     return out[0] if len(out) == 1 else out
 
 
+def ws_estimate_host(images: torch.Tensor, predictor, weighted: int = 0, clip: bool = True, correct_bias: bool = False,
+                     device=None, return_l1: bool = False):
+    """End-to-end variant for HOST images: (B,1,H,W) or (B,H,W) uint8 CPU tensor (pinned memory makes the copies
+    asynchronous). The library copies chunks H2D on a side stream while the previous chunk computes and copies
+    beta_hat / l1 back; returns CPU tensors. crop=1 semantics (attack / predict_unet)."""
+    if images.is_cuda or images.dtype != torch.uint8:
+        raise ValueError("ws_estimate_host takes a uint8 CPU tensor")
+    if images.dim() == 4:
+        images = images[:, 0]
+    images = images.contiguous()
+    B, H, W = images.shape
+    dev = filters._device(device)
+    lib = _native.load()
+    beta = torch.empty(B, dtype=torch.float32)
+    l1 = torch.empty(B, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        if isinstance(predictor, str):
+            if predictor not in _native.PRED_KINDS:
+                raise KeyError(predictor)
+            _native.check(lib.wsu_filter_ws_estimate_host(
+                dev.index, ctypes.c_void_p(images.data_ptr()), _native.PRED_KINDS[predictor], int(weighted), int(bool(clip)),
+                int(bool(correct_bias)), ctypes.c_void_p(beta.data_ptr()), ctypes.c_void_p(l1.data_ptr()) if return_l1 else None,
+                B, H, W), 'wsu_filter_ws_estimate_host')
+        elif isinstance(predictor, UNet):
+            if correct_bias:
+                raise NotImplementedError("correct_bias with a UNet predictor: use ws_estimate on device tensors")
+            _native.check(lib.wsu_unet_ws_estimate_host(
+                predictor.native_handle(dev), ctypes.c_void_p(images.data_ptr()), B, H, W, int(weighted), int(bool(clip)), 1,
+                ctypes.c_void_p(beta.data_ptr()), ctypes.c_void_p(l1.data_ptr()) if return_l1 else None),
+                'wsu_unet_ws_estimate_host')
+        else:
+            raise TypeError("predictor must be a ws_unet_b200 UNet or one of " + str(list(_native.PRED_KINDS)))
+    return (beta, l1) if return_l1 else beta
+
+
 def ws_from_prediction(images: torch.Tensor, x_hat: torch.Tensor, weighted: int = 0, clip: bool = True, crop: int = 1,
                        x_bias: typing.Optional[torch.Tensor] = None, return_l1: bool = False):
     """WS reduction against caller-supplied predictions in pixel units: x_hat (B,H,W) or cropped (B,H-2,W-2)."""

@@ -277,32 +277,34 @@ __global__ void __launch_bounds__(kFastThreads) filter_ws_fast_kernel(const uint
   const int y0 = 1 + strip * kFastRows;
   const int yend = min(y0 + kFastRows, H - 1);
   const uint8_t* base = img + size_t(b) * H * W;
-  const bool need_l = (lane == 0) && active && x > 0;
-  const bool need_r = (lane == 31) && active && (x + 4 < W);
   bool inside[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) inside[c] = active && (x + c >= 1) && (x + c <= W - 2);
 
   int top[6], mid[6], tsq[6], msq[6];
-  auto fetch = [&](int y, uint32_t& w, uint32_t& le, uint32_t& re) {
-    const uint8_t* row = base + size_t(y) * W;
-    w = active ? __ldg(reinterpret_cast<const uint32_t*>(row + x)) : 0u;
-    le = need_l ? uint32_t(__ldg(row + x - 1)) : 0u;
-    re = need_r ? uint32_t(__ldg(row + x + 4)) : 0u;
+  // own aligned word plus the words left and right of it (immediate offsets from one row pointer, L1 hits)
+  const bool has_l = active && x > 0, has_r = active && (x + 4 < W);
+  const uint8_t* rp = base + size_t(y0 - 1) * W + (active ? x : 0);
+  int yrow = y0 - 1;
+  auto fetch = [&](uint32_t& w, uint32_t& lw, uint32_t& rw) {
+    w = active ? __ldg(reinterpret_cast<const uint32_t*>(rp)) : 0u;
+    lw = has_l ? __ldg(reinterpret_cast<const uint32_t*>(rp - 4)) : 0u;
+    rw = has_r ? __ldg(reinterpret_cast<const uint32_t*>(rp + 4)) : 0u;
+    if (yrow < H - 1) rp += W;
+    ++yrow;
   };
-  auto unpack = [&](uint32_t w, uint32_t le, uint32_t re, int (&v)[6]) {
-    const uint32_t lw = __shfl_up_sync(0xffffffffu, w, 1), rw = __shfl_down_sync(0xffffffffu, w, 1);
-    v[0] = int(lane == 0 ? le : (lw >> 24));
+  auto unpack = [&](uint32_t w, uint32_t lw, uint32_t rw, int (&v)[6]) {
+    v[0] = int(lw >> 24);
     v[1] = int(w & 0xffu);
     v[2] = int((w >> 8) & 0xffu);
     v[3] = int((w >> 16) & 0xffu);
     v[4] = int(w >> 24);
-    v[5] = int(lane == 31 ? re : (rw & 0xffu));
+    v[5] = int(rw & 0xffu);
   };
   {
     uint32_t w0, l0, r0, w1, l1, r1;
-    fetch(y0 - 1, w0, l0, r0);
-    fetch(y0, w1, l1, r1);
+    fetch(w0, l0, r0);
+    fetch(w1, l1, r1);
     unpack(w0, l0, r0, top);
     unpack(w1, l1, r1, mid);
     if (WEIGHTED) {
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(kFastThreads) filter_ws_fast_kernel(const uint
   for (int yc = y0; yc < yend; yc += 6) {
     uint32_t w[6], le[6], re[6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r) fetch(min(yc + r + 1, H - 1), w[r], le[r], re[r]);
+    for (int r = 0; r < 6; ++r) fetch(w[r], le[r], re[r]);
 #pragma unroll
     for (int r = 0; r < 6; ++r) {
       int bot[6], bsq[6];
@@ -341,8 +343,18 @@ __global__ void __launch_bounds__(kFastThreads) filter_ws_fast_kernel(const uint
             acc_l1 += abs(e);
             if (WEIGHTED) {
               const int q8 = vq[c - 1] + vq[c] + vq[c + 1] + msq[c - 1] + msq[c + 1];
-              const float wgt = ws_weight(WEIGHTED, float(s8), float(q8));
-              facc_r = fmaf(wgt, float(de), facc_r);
+              // 5 + var = (320 + 8*S2 - S1^2) / 64 exactly (integers < 2^23); the common factor 64 cancels in
+              // sum(w r) / sum(w), so w = 1/D (weighted) or D (anti-weighted). Integers are converted with the
+              // 2^23 magic-number trick (no I2F), the reciprocal is MUFU.RCP + one Newton step (<= 1 ulp).
+              const float dd = __int_as_float(0x4B000000 | (320 + 8 * q8 - s8 * s8)) - 8388608.f;
+              float wgt = dd;
+              if (WEIGHTED == WS_WEIGHTED) {
+                float r;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dd));
+                wgt = r * fmaf(-dd, r, 2.f);
+              }
+              const float fde = __int_as_float(0x4B000000 | (de + 4096)) - 8392704.f;
+              facc_r = fmaf(wgt, fde, facc_r);
               facc_w += wgt;
             } else {
               acc_r += de;

@@ -42,7 +42,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s at 2 GHz: far beyond any legitimate wait
+    if (clock64() - t0 > 60000000000LL) __trap();  // ~30 s at 2 GHz: far beyond any legitimate wait (incl. profiler replays)
   }
 }
 

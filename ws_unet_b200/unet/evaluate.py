@@ -50,8 +50,12 @@ def predict_unet(fname: str, model: torch.nn.Module, *, device=None, imread: typ
     """src/unet/evaluate.py:109-139: beta_hat = mean((x - x_bar)(x - x_hat)) (unweighted, unclipped) and
     l1 = mean|x - x_hat| over the 510x510 interior, computed by the fused UNet->WS kernel chain."""
     dev = _cuda(device)
-    x = imread(fname)
-    x = np.asarray(x)[..., 3:] if np.asarray(x).shape[-1] >= 4 else np.asarray(x)[..., -1:]
+    if imread is None:                      # reference default: _defs.imread4_f32 -> (H,W,4) with luma in channel 3
+        from ..dataset import imread_gray_u8 as imread
+    x = np.asarray(imread(fname))
+    if x.ndim == 2:
+        x = x[..., None]
+    x = x[..., 3:] if x.shape[-1] >= 4 else x[..., -1:]
     img = torch.from_numpy(np.ascontiguousarray(x[..., 0]).astype(np.uint8)).to(dev)[None, None]
     img = _center_crop_512(img).contiguous()
     beta, l1 = _ws.ws_estimate(img, model, weighted=0, clip=False, crop=1, return_l1=True)

@@ -32,7 +32,12 @@ def test_native_library_is_the_path(cuda_dev):
     m = _model(2, 1, cuda_dev)
     _native.load().wsu_launch_count(1)
     m(torch.rand(1, 1, 32, 32, device=cuda_dev))
-    assert _native.load().wsu_launch_count(0) == 1 + 11  # e11 + 11 tensor-core layers (e12..e32, upconv3, d31, d32, upconv4, d41, d42)
+    # e11 + 11 tensor-core layers (e12..e32, upconv3, d31, d32, upconv4, d41, d42)
+    assert _native.load().wsu_launch_count(0) == 12
+    _native.check(_native.load().wsu_set_option(m.native_handle(cuda_dev), b'fuse_e11', 1))
+    _native.load().wsu_launch_count(1)
+    m(torch.rand(1, 1, 32, 32, device=cuda_dev))
+    assert _native.load().wsu_launch_count(0) == 11   # e11 computed inside e12's producer warps
 
 
 # ------------------------------------------------------------------------------------------------ UNet forward
@@ -61,9 +66,10 @@ def test_unet_layers_and_reflect_halo_match_oracle(cuda_dev):
     sd = uo.numpy_weights(2, seed=9)
     m = _model(2, 9, cuda_dev)
     x = np.random.default_rng(3).random((2, 1, 48, 80), dtype=np.float32)
+    lib = _native.load()
+    _native.check(lib.wsu_set_option(m.native_handle(cuda_dev), b'fuse_e11', 0))   # materialise e11 so it can be inspected
     m(torch.from_numpy(x).to(cuda_dev))
     _, acts = uo.unet_forward(sd, x, 2, keep=True)
-    lib = _native.load()
     for name in ['e11', 'e12', 'p1', 'e21', 'e22', 'p2', 'e31', 'e32', 'u3', 'd31', 'd32', 'u4', 'd41']:
         ref = acts[name]
         ref_h = np.pad(ref, ((0, 0), (0, 0), (1, 1), (1, 1)), mode='reflect')
@@ -284,6 +290,14 @@ def test_kernel_variants_agree(cuda_dev):
     lib.wsu_set_option(h, b'upconv_resident', 1)
     assert np.abs(outs[(1, 1, 1)] - outs[(0, 0, 0)]).max() * 255 < 1e-4
     assert np.array_equal(outs[(1, 2, 1)], outs[(1, 0, 1)])   # CTA pairs issue the same MMAs: bit-identical
+    # e11 fused into e12's producer warps vs materialised in HBM: same arithmetic, same bits (also on uint8 input)
+    img8 = torch.randint(0, 256, (2, 1, 80, 112), dtype=torch.uint8, device=cuda_dev)
+    for inp in (xd, img8):
+        lib.wsu_set_option(h, b'fuse_e11', 1)
+        y_fused = m(inp)
+        lib.wsu_set_option(h, b'fuse_e11', 0)
+        assert torch.equal(y_fused, m(inp))
+    lib.wsu_set_option(h, b'fuse_e11', 1)
     with pytest.raises(ValueError):
         _native.check(lib.wsu_set_option(h, b'no_such_option', 1))
 

@@ -29,6 +29,7 @@ def layer_report(nsteps, B, H, Wd, seed=0):
     torch.manual_seed(seed)
     model = W.get_model(f'unet_{nsteps}', 1).to(dev)
     x = torch.rand(B, 1, H, Wd, device=dev)
+    _native.load().wsu_set_option(model.native_handle(dev), b'fuse_e11', 0)   # keep e11 inspectable
     y = model(x)
     torch.cuda.synchronize()
     yref, acts = reference_forward(model, x, keep=True)

@@ -427,7 +427,7 @@ struct HCfg {
   static constexpr int W_PER_TAP = STACKED ? 1 : 2;          // ring slots consumed per tap
   static constexpr int SW = 4;
   static constexpr int BIAS_BYTES = (N_TILE == 64) ? 256 : 4096;
-  static constexpr int SMEM = SA * kHaloABytes + SW * W_BYTES + kScratchBytes + 1024 + BIAS_BYTES + 256;
+  static constexpr int SMEM = SA * kHaloABytes + SW * W_BYTES + kScratchBytes + 1024 + BIAS_BYTES + 256 + 1024 /*patch*/;
 };
 
 struct BoxCoord {
@@ -445,10 +445,22 @@ __device__ __forceinline__ BoxCoord decode_box(const ConvParams& p, int s) {
   return c;
 }
 
-template <int N_TILE, int EPI>
-__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ ConvParams p) {
+// FUSE: the layer's input is the first convolution e11 (Cin = 1, K = 9) of the image itself. Three extra warps compute
+// each haloed box of relu(e11(image)) straight into the activation ring (split-bf16, swizzled exactly as TMA would have
+// written it), so e11's 67 MB/image feature map is never written to or read from HBM.
+constexpr int kFuseWarps = 3, kFuseThreads = kFuseWarps * 32;
+
+__device__ __forceinline__ int reflect_clamp(int v, int n) {
+  v = v < 0 ? -v : (v >= n ? 2 * n - 2 - v : v);
+  return min(max(v, 0), n - 1);
+}
+
+template <int N_TILE, int EPI, bool FUSE = false>
+__global__ void __launch_bounds__(kHaloThreads + (FUSE ? kFuseThreads : 0), 1)
+conv_halo_kernel(const __grid_constant__ ConvParams p) {
   using C = HCfg<N_TILE>;
   constexpr int M_SUB = C::M_SUB;
+  constexpr int kThreadsAll = kHaloThreads + (FUSE ? kFuseThreads : 0);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -464,6 +476,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint64_t* acc_full = w_empty + C::SW;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sPatch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // FUSE: 20 x 12 image patch
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -477,15 +490,77 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  for (int i = threadIdx.x; i < p.cout && i < C::BIAS_BYTES / 4; i += kHaloThreads) sBias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.cout && i < C::BIAS_BYTES / 4; i += kThreadsAll) sBias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (FUSE && warp >= 11) {
+    // ===================================================== fused e11 producer (3 warps): compute the haloed box in place
+    const int t = threadIdx.x - 11 * 32;
+    const int q = t & 7;                       // this thread's 8 output channels = one 16-byte piece of a pixel row
+    float wr[8][9], bs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      bs[i] = p.fuse_b[q * 8 + i];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) wr[i][k] = p.fuse_w[(q * 8 + i) * 9 + k];
+    }
+    const int H = p.H, W = p.W;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const int s0 = (item / p.n_tiles) * M_SUB;
+      const int nsub = min(M_SUB, p.total_sub - s0);
+      for (int j = 0; j < nsub; ++j) {
+        const BoxCoord bc = decode_box(p, s0 + j);
+        mbar_wait(&a_empty[as], aph ^ 1);
+        // image patch rows y0-2 .. y0+17, cols x0-2 .. x0+9 (reflect-resolved, scaled to [0,1] like e11 does)
+        for (int i = t; i < 240; i += kFuseThreads) {
+          const int yy = reflect_clamp(bc.y0 - 2 + i / 12, H), xx = reflect_clamp(bc.x0 - 2 + i % 12, W);
+          const size_t o = (size_t(bc.b) * H + yy) * W + xx;
+          sPatch[i] = p.fuse_img_is_float ? static_cast<const float*>(p.fuse_img)[o]
+                                          : __fdiv_rn(float(static_cast<const uint8_t*>(p.fuse_img)[o]), 255.f);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kFuseThreads) : "memory");
+        uint8_t* slot = sA + as * kHaloABytes;
+#pragma unroll 1
+        for (int task = t; task < kHaloRows * 8; task += kFuseThreads) {
+          const int pix = task >> 3;
+          const int py = pix / (kHaloTW + 2), px = pix - py * (kHaloTW + 2);
+          // halo pixels take the value of their mirror image (reflect padding of e11's output, unet.py:73)
+          const int yy = reflect_clamp(bc.y0 - 1 + py, H), xx = reflect_clamp(bc.x0 - 1 + px, W);
+          const int ry = min(max(yy - (bc.y0 - 2), 1), 18), rx = min(max(xx - (bc.x0 - 2), 1), 10);
+          const float* win = sPatch + (ry - 1) * 12 + (rx - 1);
+          float acc[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = bs[i];
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const float v = win[dy * 12 + dx];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, wr[i][dy * 3 + dx], acc[i]);
+            }
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_pack2(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f), h[i], l[i]);
+          // SWIZZLE_128B on absolute address bits: the lo plane starts 180 rows in, i.e. at row phase (pix + 4) & 7
+          *reinterpret_cast<uint4*>(slot + pix * 128 + ((q ^ (pix & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(slot + kHaloRows * 128 + pix * 128 + ((q ^ ((pix + 4) & 7)) << 4)) =
+              make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+        asm volatile("bar.sync 1, %0;" ::"n"(kFuseThreads) : "memory");
+        if (t == 0) mbar_arrive(&a_full[as]);
+        if (++as == C::SA) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
     // ===================================================== activation producer: one haloed box per (box, channel block)
-    if (elect_one()) {
+    if (!FUSE && elect_one()) {
       int as = 0;
       uint32_t aph = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -644,6 +719,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 template <int N_TILE, int EPI>
 cudaError_t launch_halo_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   const int grid = p.total_items < num_sms ? p.total_items : num_sms;
+  if constexpr (N_TILE == 64 && EPI == EPI_ACT) {
+    if (p.fuse_img) {
+      if (p.cblocks != 1) return cudaErrorInvalidValue;
+      conv_halo_kernel<64, EPI_ACT, true><<<grid, kHaloThreads + kFuseThreads, HCfg<64>::SMEM, stream>>>(p);
+      return cudaGetLastError();
+    }
+  }
   conv_halo_kernel<N_TILE, EPI><<<grid, kHaloThreads, HCfg<N_TILE>::SMEM, stream>>>(p);
   return cudaGetLastError();
 }
@@ -1058,6 +1140,8 @@ cudaError_t conv_mma_init() {
   e = cudaFuncSetAttribute(conv_mma_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo_kernel<64, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<64>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo_kernel<64, EPI_ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<64>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo_kernel<128, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, HCfg<128>::SMEM);
   if (e != cudaSuccess) return e;

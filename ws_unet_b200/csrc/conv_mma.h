@@ -32,6 +32,12 @@ struct alignas(64) ConvParams {
   int sub_x, sub_y;      // boxes per image row / column
   int total_sub;         // B * sub_y * sub_x
   int total_items;       // ceil(total_sub / M_SUB) * n_tiles
+  // fused first layer (halo kernel, Cin = 64 only): when fuse_img != null the input boxes are relu(e11(image)) computed
+  // in the kernel from the image and e11's fp32 weights [64][9] / bias [64] instead of being loaded from tmapH0
+  const void* fuse_img;
+  int fuse_img_is_float;
+  const float* fuse_w;
+  const float* fuse_b;
   // EPI_ACT
   int relu;
   int upsample;          // 1: write phase (pos>>1, pos&1) of a 2x upsampled map (ConvTranspose2d k=2,s=2)

@@ -297,7 +297,6 @@ def test_kernel_variants_agree(cuda_dev):
         y_fused = m(inp)
         lib.wsu_set_option(h, b'fuse_e11', 0)
         assert torch.equal(y_fused, m(inp))
-    lib.wsu_set_option(h, b'fuse_e11', 1)
     with pytest.raises(ValueError):
         _native.check(lib.wsu_set_option(h, b'no_such_option', 1))
 

@@ -238,7 +238,8 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   if (epi == EPI_HEAD) {
     std::memcpy(p.wout, h->wout, sizeof(p.wout));
     p.bout = h->bout;
-    pl.tiles_per_img = std::max(p.tiles_x * p.tiles_y, p.sub_x * p.sub_y);  // partial records: v1 tiles or halo boxes
+    // partial records per image: 8 per super-tile (per-tap kernel) or 4 per box (halo kernels), whichever is larger
+    pl.tiles_per_img = std::max(2 * p.tiles_x * p.tiles_y, p.sub_x * p.sub_y);
   }
   pl.convs.push_back({p, {lw.n_tile, epi}});
   pl.conv_names.push_back(lname);
@@ -265,10 +266,21 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   return WSU_OK;
 }
 
+int build_plan_impl(wsu_context* h, int mb, int H, int W);
+
 int build_plan(wsu_context* h, int mb, int H, int W) {
   if (h->plan && h->plan->mb >= mb && h->plan->H == H && h->plan->W == W) return WSU_OK;
   if (h->plan) { cudaDeviceSynchronize(); free_plan(h->plan.get()); }
   h->plan.reset(new Plan());
+  const int rc = build_plan_impl(h, mb, H, W);
+  if (rc != WSU_OK) {  // never keep a half-built plan around
+    free_plan(h->plan.get());
+    h->plan.reset();
+  }
+  return rc;
+}
+
+int build_plan_impl(wsu_context* h, int mb, int H, int W) {
   Plan& pl = *h->plan;
   pl.mb = mb; pl.H = H; pl.W = W;
   const int n = h->nsteps;

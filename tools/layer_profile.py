@@ -42,7 +42,10 @@ def main():
     res = {}
     variant = sys.argv[3] if len(sys.argv) > 3 else 'halo'   # what the left column runs: 'halo' or 'pair'
     for halo in (1, 0):
-        if variant == 'pair':
+        if variant == 'pair2':     # every 3x3 layer as CTA pairs vs the default (Cout >= 128 only)
+            lib.wsu_set_option(h, b'halo', 1)
+            lib.wsu_set_option(h, b'cta_pair', 2 if halo else 1)
+        elif variant == 'pair':
             lib.wsu_set_option(h, b'halo', 1)
             lib.wsu_set_option(h, b'cta_pair', halo)
         else:
@@ -51,7 +54,7 @@ def main():
         beta, yhat = W.ws_estimate(imgs[:8], model, return_prediction=True)
         torch.cuda.synchronize()
         res[halo] = (profile(model, imgs, lib, h, reps), beta, yhat)
-    print(f'left column = {variant}, right column = ' + ('halo (single CTA)' if variant == 'pair' else 'per-tap'))
+    print(f'left column = {variant}, right column = ' + {'pair': 'halo (single CTA)', 'pair2': 'pair for Cout>=128 only'}.get(variant, 'per-tap'))
     print('beta bit-equal:', torch.equal(res[1][1], res[0][1]), ' max|d beta| =', (res[1][1] - res[0][1]).abs().max().item(),
           ' max|d yhat| px =', ((res[1][2] - res[0][2]).abs().max() * 255).item())
     names = res[1][0][0]

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -517,6 +518,10 @@ int wsu_create(wsu_handle* out, int device, int nsteps, int in_channels, int out
   h->in_ch = in_channels;
   h->out_ch = out_channels;
   h->num_sms = prop.multiProcessorCount;
+  // experiment switches (profiling runs): same meaning as the wsu_set_option keys
+  if (const char* e = std::getenv("WSU_CTA_PAIR")) h->use_pair = std::atoi(e);
+  if (const char* e = std::getenv("WSU_FUSE_E11")) h->fuse_e11 = std::atoi(e) != 0;
+  if (const char* e = std::getenv("WSU_HALO")) h->use_halo = std::atoi(e) != 0;
   *out = h;
   return WSU_OK;
 }

@@ -147,6 +147,7 @@ struct wsu_context {
   // is off by default.
   bool fuse_e11 = false;
   int use_pair = 1;  // 3x3 layers as CTA pairs (tcgen05 cta_group::2): 0 never, 1 Cout>=128 layers (measured win), 2 all
+  int l2_prefetch = 0;    // halo kernels prefetch the next item's boxes into L2 (option "l2_prefetch"); measured 1 % slower
   bool use_upres = true;  // transposed convs through upconv_res_kernel (option "upconv_resident")
   bool use_halo = true;  // 3x3 layers through conv_halo_kernel (option "halo"; 0 = per-tap reload kernel, for A/B runs)
 };
@@ -402,6 +403,7 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
     ConvParams p = pl.convs[i].first;
     const int n_tile = pl.convs[i].second.first, epi = pl.convs[i].second.second;
     const bool halo = h->use_halo && p.ntaps == 9;
+    p.l2_prefetch = h->l2_prefetch;
     if (nimg != pl.mb) {
       p.B = nimg;
       p.total_tiles = nimg * p.tiles_y * p.tiles_x * p.n_tiles * p.npos;
@@ -556,6 +558,10 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
   }
   if (!std::strcmp(key, "fuse_e11")) {
     h->fuse_e11 = value != 0;
+    return WSU_OK;
+  }
+  if (!std::strcmp(key, "l2_prefetch")) {
+    h->l2_prefetch = value != 0;
     return WSU_OK;
   }
   if (!std::strcmp(key, "cta_pair")) {

@@ -566,10 +566,19 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const int s0 = (item / p.n_tiles) * M_SUB;
         const int nsub = min(M_SUB, p.total_sub - s0);
+        // the boxes of this CTA's NEXT item are pulled into L2 now: under heavy HBM write traffic a cold 45 KB box load
+        // takes longer than the ring can cover
+        const int item_n = item + gridDim.x;
+        const int s0_n = (item_n / p.n_tiles) * M_SUB;
+        const int nsub_n = (p.l2_prefetch && item_n < p.total_items) ? min(M_SUB, p.total_sub - s0_n) : 0;
         for (int c = 0; c < p.cblocks; ++c) {
           const bool src0 = c < p.cblocks0;
           const CUtensorMap* tm = src0 ? &p.tmapH0 : &p.tmapH1;
           const int ch = (src0 ? c : c - p.cblocks0) * 64;
+          for (int j = 0; j < nsub_n; ++j) {
+            const BoxCoord bn = decode_box(p, s0_n + j);
+            tma_prefetch_5d(tm, ch, bn.x0, bn.y0, bn.b, 0);
+          }
           for (int j = 0; j < nsub; ++j) {
             const BoxCoord bc = decode_box(p, s0 + j);
             mbar_wait(&a_empty[as], aph ^ 1);
@@ -838,10 +847,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
       for (int item = pair; item < items; item += npairs) {
         const int s0 = (item / p.n_tiles) * (2 * M_SUB);
         const int nslot = min(M_SUB, (p.total_sub - s0 + 1) / 2);
+        const int item_n = item + npairs;
+        const int s0_n = (item_n / p.n_tiles) * (2 * M_SUB);
+        const int nslot_n = (p.l2_prefetch && item_n < items) ? min(M_SUB, (p.total_sub - s0_n + 1) / 2) : 0;
         for (int c = 0; c < p.cblocks; ++c) {
           const bool src0 = c < p.cblocks0;
           const CUtensorMap* tm = src0 ? &p.tmapH0 : &p.tmapH1;
           const int ch = (src0 ? c : c - p.cblocks0) * 64;
+          for (int j = 0; j < nslot_n; ++j) {   // L2 warm-up of this CTA's boxes of the pair's next item
+            const BoxCoord bn = decode_box(p, min(s0_n + 2 * j + int(rank), p.total_sub - 1));
+            tma_prefetch_5d(tm, ch, bn.x0, bn.y0, bn.b, 0);
+          }
           for (int j = 0; j < nslot; ++j) {
             const BoxCoord bc = decode_box(p, min(s0 + 2 * j + int(rank), p.total_sub - 1));
             mbar_wait(&a_empty[as], aph ^ 1);

@@ -38,6 +38,7 @@ struct alignas(64) ConvParams {
   int fuse_img_is_float;
   const float* fuse_w;
   const float* fuse_b;
+  int l2_prefetch;       // halo kernels: warm L2 with the boxes of the CTA's next work item
   // EPI_ACT
   int relu;
   int upsample;          // 1: write phase (pos>>1, pos&1) of a 2x upsampled map (ConvTranspose2d k=2,s=2)

@@ -812,9 +812,14 @@ int wsu_filter_ws_estimate(int device, const void* img_dev, int img_dtype, int k
   int records = filter_ws_strips(H);
   const bool fast = filter_ws_fast_ok(img_dev, img_dtype == WSU_F32, W, kind, correct_bias, nullptr);
   const bool packed = fast && weighted == WSU_UNWEIGHTED && l1_dev == nullptr;
-  if (fast) records = packed ? filter_ws_packed_records(H, W) : filter_ws_fast_records(H, W);
+  // WSU_EST_KERNEL=packed keeps the 16-bit-lane kernel for A/B runs; default is the adjoint (parity-plane) kernel
+  static const bool prefer_packed = [] { const char* e = std::getenv("WSU_EST_KERNEL"); return e && !std::strcmp(e, "packed"); }();
+  const bool adjoint = packed && !prefer_packed && filter_ws_adjoint_ok(img_dev, H, W);
+  if (fast) records = adjoint ? filter_ws_adjoint_records(H, W) : packed ? filter_ws_packed_records(H, W) : filter_ws_fast_records(H, W);
   CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partials), size_t(B) * records * kPartialSlots * 4, st));
-  if (packed)
+  if (adjoint)
+    LAUNCH_TRY(launch_filter_ws_adjoint(img_dev, B, H, W, kind, partials, st));
+  else if (packed)
     LAUNCH_TRY(launch_filter_ws_packed(img_dev, B, H, W, kind, partials, st));
   else if (fast)
     LAUNCH_TRY(launch_filter_ws_fast(img_dev, B, H, W, kind, weighted, partials, st));

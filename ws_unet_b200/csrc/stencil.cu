@@ -523,6 +523,140 @@ __global__ void __launch_bounds__(kFastThreads) filter_ws_packed_kernel(const ui
   }
 }
 
+// ------------------------------------------------------------------------------------------------ adjoint filter WS
+// Unweighted KB / AVG beta_hat through the adjoint of the predictor stencil. With s = x - x_bar = +-1 on the interior
+// (0 elsewhere) and R = D * (x - x_hat) = K (*) x (K = 4*delta - 4*KB or 8*delta - 8*AVG, symmetric, sums to 0):
+//     sum_interior s * R  =  sum_{q in image} x_q * (K (*) s)_q,
+// so the stencil is applied to the PARITY plane instead of the pixels: e = s + 1 in {0, 1, 2} (1 outside the
+// interior and outside the image; a constant is annihilated by K) fits four pixels per 32-bit register as bytes,
+// both separable passes stay inside a byte (KB: T = e_l + e_r - 2e + 4 in [0,8], G' = T_u + T_d - 2T + 16 in [0,32];
+// AVG: T = e_l + e + e_r in [0,6], G' = 9e + 16 - (T_u + T + T_d) in [0,32]) and the pixel side is two dp4a per word:
+// sum x*G' and sum x (the +16 bias is removed as 16 * sum x). Exact integer arithmetic end to end; about 2.6 thread
+// instructions per pixel instead of 13 in the packed kernel. A warp walks a 512-pixel-wide strip of kAdjRows rows
+// (16 pixels = one 16-byte load per lane and row); neighbour words come from warp shuffles.
+constexpr int kAdjRows = 64;    // G rows per warp task (T rows: + 2)
+constexpr int kAdjWarps = 8;    // warps per CTA = images per CTA (all warps of a CTA share the row range)
+constexpr int kAdjUnroll = 8;   // rows fetched per batch in the steady state
+constexpr uint32_t kOnes = 0x01010101u;
+
+template <int KIND>
+struct AdjState {
+  uint32_t M[4], C[4];                       // parity -> e: e = (w & M) * 2 + C
+  uint32_t Tm1[4], Tm2[4], wm1[4], Em1[4];   // previous two T rows, previous pixel row, 9e+16 of the previous row (AVG)
+  uint32_t acc = 0u, accx = 0u;
+  int lane;
+
+  // one image row: w = 16 pixels of this lane, (exl, exr) = e words of the strip's outer neighbours (lanes 0 / 31)
+  template <bool kInterior, bool kEmit>
+  __device__ __forceinline__ void row(const uint4& wv, uint32_t exl, uint32_t exr) {
+    const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+    uint32_t e[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e[i] = kInterior ? (w[i] & M[i]) * 2u + C[i] : kOnes;
+    uint32_t eL = kOnes, eR = kOnes;
+    if (kInterior) {
+      eL = __shfl_up_sync(0xffffffffu, e[3], 1);
+      eR = __shfl_down_sync(0xffffffffu, e[0], 1);
+      if (lane == 0) eL = exl;
+      if (lane == 31) eR = exr;
+    }
+    uint32_t T[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t el = __funnelshift_l(i ? e[i - 1] : eL, e[i], 8);      // e of the left neighbours
+      const uint32_t er = __funnelshift_r(e[i], i < 3 ? e[i + 1] : eR, 8);  // e of the right neighbours
+      T[i] = (KIND == PRED_KB) ? el + er + (0x04040404u - 2u * e[i]) : el + er + e[i];
+    }
+    if (kEmit) {  // G of the previous row is complete
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t G = (KIND == PRED_KB) ? Tm2[i] + T[i] + (0x10101010u - 2u * Tm1[i])
+                                             : Em1[i] - (Tm2[i] + Tm1[i] + T[i]);
+        acc = __dp4a(wm1[i], G, acc);
+        accx = __dp4a(wm1[i], kOnes, accx);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      Tm2[i] = Tm1[i]; Tm1[i] = T[i]; wm1[i] = w[i];
+      if (KIND != PRED_KB) Em1[i] = 9u * e[i] + 0x10101010u;
+    }
+  }
+};
+
+template <int KIND, bool kMulti>
+__global__ void __launch_bounds__(kAdjWarps * 32, 3) filter_ws_adjoint_kernel(const uint8_t* __restrict__ img, int B, int H,
+                                                                              int W, float* __restrict__ partials,
+                                                                              int rstrips, int cstrips) {
+  const int lane = threadIdx.x & 31;
+  const int cs = kMulti ? blockIdx.x % cstrips : 0;
+  const int rs = (blockIdx.x / cstrips) % rstrips;
+  const int b = (blockIdx.x / (cstrips * rstrips)) * kAdjWarps + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int x = cs * 512 + lane * 16;
+  const bool active = x < W;  // W % 16 == 0: a lane's 16 pixels are all inside or all outside
+  const int r0 = rs * kAdjRows, r1 = min(r0 + kAdjRows, H);  // this CTA's warps own G rows [r0, r1) of their images
+
+  AdjState<KIND> st;
+  st.lane = lane;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    st.M[i] = active ? kOnes : 0u; st.C[i] = active ? 0u : kOnes;   // lanes right of the image hold e = 1, w = 0
+    st.Tm1[i] = st.Tm2[i] = st.wm1[i] = st.Em1[i] = 0u;
+  }
+  if (active && x == 0) { st.M[0] &= ~0xffu; st.C[0] |= 0x01u; }                        // column 0
+  if (active && x + 16 == W) { st.M[3] &= ~0xff000000u; st.C[3] |= 0x01000000u; }       // column W-1
+  // strip edges inside the image (W > 512 only): lane 0 / lane 31 fetch the neighbouring word themselves
+  const bool edge_l = kMulti && (lane == 0) && active && x > 0;
+  const bool edge_r = kMulti && (lane == 31) && active && (x + 16 < W);
+  const int edge_off = edge_l ? -4 : 16;
+
+  const uint8_t* rp = img + size_t(b) * H * W + (active ? x : 0);   // row pointer of the next row to fetch
+  auto fetch = [&](uint4& wv, uint32_t& ex) {
+    wv = active ? __ldg(reinterpret_cast<const uint4*>(rp)) : make_uint4(0u, 0u, 0u, 0u);
+    if (kMulti) ex = (edge_l || edge_r) ? (__ldg(reinterpret_cast<const uint32_t*>(rp + edge_off)) & kOnes) * 2u : kOnes;
+    else ex = kOnes;
+    rp += W;
+  };
+  // generic row (top / bottom of the strip, image border rows): runtime row class, one row at a time
+  auto slow_row = [&](int y, bool emit) {
+    uint4 wv = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t ex = kOnes;
+    if (y >= 0 && y < H) fetch(wv, ex);
+    const bool interior = (y > 0) && (y < H - 1);
+    if (interior) { if (emit) st.template row<true, true>(wv, ex, ex); else st.template row<true, false>(wv, ex, ex); }
+    else          { if (emit) st.template row<false, true>(wv, ex, ex); else st.template row<false, false>(wv, ex, ex); }
+  };
+
+  if (r0 > 0) rp += size_t(r0 - 1) * W;
+  slow_row(r0 - 1, false);
+  slow_row(r0, false);
+  int y = r0 + 1;
+  const int ylast = min(r1, H - 2);   // rows y..ylast are interior rows and each completes the G row above it
+  for (; y + kAdjUnroll - 1 <= ylast; y += kAdjUnroll) {
+    uint4 wv[kAdjUnroll];
+    uint32_t ex[kAdjUnroll];
+#pragma unroll
+    for (int r = 0; r < kAdjUnroll; ++r) fetch(wv[r], ex[r]);
+#pragma unroll
+    for (int r = 0; r < kAdjUnroll; ++r) st.template row<true, true>(wv[r], ex[r], ex[r]);
+  }
+  for (; y <= r1; ++y) slow_row(y, true);
+
+  // per lane: sum x*G' <= 16 px * 66 rows * 255 * 32 and 16 * sum x likewise; the warp total stays below 2^31
+  const int mine = int(st.acc) - 16 * int(st.accx);
+  const int sr = __reduce_add_sync(0xffffffffu, mine);
+  if (lane == 0) {
+    constexpr float kScale = (KIND == PRED_KB) ? 0.25f : 0.125f;
+    float* dst = partials + ((size_t(b) * rstrips + rs) * cstrips + cs) * 2 * kPartialSlots;
+    const int sr_lo = sr & 0xfff;
+    const int n = (rs == 0 && cs == 0) ? (H - 2) * (W - 2) : 0;   // the pixel count rides on the image's first task
+    const int n_lo = n & 0xfff;
+    dst[0] = float(sr - sr_lo) * kScale; dst[1] = float(n - n_lo); dst[2] = 0.f; dst[3] = 0.f;
+    dst[4] = float(sr_lo) * kScale;      dst[5] = float(n_lo);     dst[6] = 0.f; dst[7] = 0.f;
+  }
+}
+
 // WS terms against a caller-supplied prediction (pixel units), grid-stride per image chunk.
 template <bool kFloatIn>
 __global__ void __launch_bounds__(256) ws_from_pred_kernel(const void* __restrict__ img, const float* __restrict__ xhat,
@@ -706,6 +840,27 @@ cudaError_t launch_filter_ws_packed(const void* img, int B, int H, int W, int ki
   const int grid = B * strips * xtiles;
   if (kind == PRED_KB) filter_ws_packed_kernel<PRED_KB><<<grid, kFastThreads, 0, stream>>>(im, H, W, partials, strips, xtiles);
   else filter_ws_packed_kernel<PRED_AVG><<<grid, kFastThreads, 0, stream>>>(im, H, W, partials, strips, xtiles);
+  return cudaGetLastError();
+}
+
+bool filter_ws_adjoint_ok(const void* img, int H, int W) {
+  return (W % 16 == 0) && (reinterpret_cast<uintptr_t>(img) % 16 == 0) && H >= 3 &&
+         double(H - 2) * double(W - 2) < 2147483648.0;
+}
+int filter_ws_adjoint_records(int H, int W) { return ((H + kAdjRows - 1) / kAdjRows) * ((W + 511) / 512) * 2; }
+cudaError_t launch_filter_ws_adjoint(const void* img, int B, int H, int W, int kind, float* partials, cudaStream_t stream) {
+  const int rstrips = (H + kAdjRows - 1) / kAdjRows, cstrips = (W + 511) / 512;
+  const long long ctas = (long long)((B + kAdjWarps - 1) / kAdjWarps) * rstrips * cstrips;
+  if (ctas > 0x7fffffffll) return cudaErrorInvalidValue;
+  const uint8_t* im = static_cast<const uint8_t*>(img);
+  const int grid = int(ctas), thr = kAdjWarps * 32;
+  if (kind == PRED_KB) {
+    if (cstrips > 1) filter_ws_adjoint_kernel<PRED_KB, true><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips);
+    else filter_ws_adjoint_kernel<PRED_KB, false><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips);
+  } else {
+    if (cstrips > 1) filter_ws_adjoint_kernel<PRED_AVG, true><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips);
+    else filter_ws_adjoint_kernel<PRED_AVG, false><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips);
+  }
   return cudaGetLastError();
 }
 

@@ -16,6 +16,10 @@ cudaError_t launch_filter_ws_fast(const void* img, int B, int H, int W, int kind
 // packed 16-bit-lane variant of the fast path: unweighted, beta_hat only (no l1)
 int filter_ws_packed_records(int H, int W);
 cudaError_t launch_filter_ws_packed(const void* img, int B, int H, int W, int kind, float* partials, cudaStream_t stream);
+// adjoint variant (stencil applied to the parity plane, dp4a against the pixels): unweighted, beta_hat only, W % 16 == 0
+bool filter_ws_adjoint_ok(const void* img, int H, int W);
+int filter_ws_adjoint_records(int H, int W);
+cudaError_t launch_filter_ws_adjoint(const void* img, int B, int H, int W, int kind, float* partials, cudaStream_t stream);
 cudaError_t launch_filter_ws(const void* img, int img_is_float, int B, int H, int W, int kind, int weighted, int want_bias,
                              float* xhat_out, float* partials, cudaStream_t stream);
 cudaError_t launch_ws_from_pred(const void* img, int img_is_float, const float* xhat, int xhat_cropped, const float* xbias,

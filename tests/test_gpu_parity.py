@@ -222,6 +222,33 @@ def test_lsb_flip_and_parity_bit_exact(cuda_dev):
     assert torch.all(W.ws_estimate(d, '1', weighted=1, clip=False) == 0)   # identity predictor => residual 0
 
 
+def test_adjoint_estimator_kernel_is_exact(cuda_dev):
+    """Unweighted KB/AVG beta_hat goes through the adjoint (parity-plane) kernel when W % 16 == 0 and through the packed
+    16-bit-lane kernel otherwise; both are integer-exact, so beta_hat must equal the exactly computed
+    float32(sum((x - x_bar) * D(x - x_hat)) / D / n) bit for bit — over ragged heights, multi-strip widths (> 512),
+    constant / saturated / checkerboard images, and a batch that does not fill the last CTA."""
+    import ws_unet_b200 as W
+    rng = np.random.default_rng(5)
+    for h, w in [(3, 16), (4, 16), (5, 32), (64, 48), (65, 512), (66, 528), (130, 1024), (200, 1040), (67, 2064), (35, 516)]:
+        img = rng.integers(0, 256, (9, 1, h, w), dtype=np.uint8)
+        img[1] = 255
+        img[2] = (rng.integers(0, 2, (h, w)) * 255).astype(np.uint8)
+        img[3] = 0
+        img[4, 0] = (np.add.outer(np.arange(h), np.arange(w)) % 2) * 255
+        d = torch.from_numpy(img).to(cuda_dev)
+        x = img[:, 0].astype(np.int64)
+        c = x[:, 1:-1, 1:-1]
+        cross = x[:, :-2, 1:-1] + x[:, 2:, 1:-1] + x[:, 1:-1, :-2] + x[:, 1:-1, 2:]
+        diag = x[:, :-2, :-2] + x[:, :-2, 2:] + x[:, 2:, :-2] + x[:, 2:, 2:]
+        sign = np.where(c & 1, 1, -1)                                  # x - (x ^ 1)
+        for name, scale, resid in (('KB', 4, 4 * c - 2 * cross + diag), ('AVG', 8, 8 * c - cross - diag)):
+            exact = (((sign * resid).sum(axis=(1, 2)) / scale) / float((h - 2) * (w - 2))).astype(np.float32)
+            got = W.ws_estimate(d, name, weighted=0, clip=False).cpu().numpy()
+            assert np.array_equal(got, exact), (h, w, name, got, exact)
+            sub = W.ws_estimate(d[2:7], name, weighted=0, clip=False).cpu().numpy()   # position in the batch is irrelevant
+            assert np.array_equal(sub, exact[2:7])
+
+
 # ------------------------------------------------------------------------------------------------ properties at full size
 def test_full_size_properties_512(cuda_dev):
     """BASELINE config 3 shape (512x512, alpha sweep) through properties: order/batch invariance (bit-exact),

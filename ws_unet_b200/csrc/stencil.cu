@@ -545,6 +545,9 @@ struct AdjState {
   uint32_t Tm1[4], Tm2[4], wm1[4], Em1[4];   // previous two T rows, previous pixel row, 9e+16 of the previous row (AVG)
   uint32_t acc = 0u, accx = 0u;
   int lane;
+  // multipliers 2 and -2 arrive as kernel arguments: with immediates the compiler strength-reduces the multiply-adds
+  // into shifts/adds on the (already busier) ALU pipe; as register operands they stay IMADs on the FMA pipe
+  uint32_t two, neg2;
 
   // one image row: w = 16 pixels of this lane, (exl, exr) = e words of the strip's outer neighbours (lanes 0 / 31)
   template <bool kInterior, bool kEmit>
@@ -552,7 +555,7 @@ struct AdjState {
     const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
     uint32_t e[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) e[i] = kInterior ? (w[i] & M[i]) * 2u + C[i] : kOnes;
+    for (int i = 0; i < 4; ++i) e[i] = kInterior ? (w[i] & M[i]) * two + C[i] : kOnes;
     uint32_t eL = kOnes, eR = kOnes;
     if (kInterior) {
       eL = __shfl_up_sync(0xffffffffu, e[3], 1);
@@ -565,12 +568,12 @@ struct AdjState {
     for (int i = 0; i < 4; ++i) {
       const uint32_t el = __funnelshift_l(i ? e[i - 1] : eL, e[i], 8);      // e of the left neighbours
       const uint32_t er = __funnelshift_r(e[i], i < 3 ? e[i + 1] : eR, 8);  // e of the right neighbours
-      T[i] = (KIND == PRED_KB) ? el + er + (0x04040404u - 2u * e[i]) : el + er + e[i];
+      T[i] = (KIND == PRED_KB) ? el + er + (e[i] * neg2 + 0x04040404u) : el + er + e[i];
     }
     if (kEmit) {  // G of the previous row is complete
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const uint32_t G = (KIND == PRED_KB) ? Tm2[i] + T[i] + (0x10101010u - 2u * Tm1[i])
+        const uint32_t G = (KIND == PRED_KB) ? Tm2[i] + T[i] + (Tm1[i] * neg2 + 0x10101010u)
                                              : Em1[i] - (Tm2[i] + Tm1[i] + T[i]);
         acc = __dp4a(wm1[i], G, acc);
         accx = __dp4a(wm1[i], kOnes, accx);
@@ -587,7 +590,8 @@ struct AdjState {
 template <int KIND, bool kMulti>
 __global__ void __launch_bounds__(kAdjWarps * 32, 3) filter_ws_adjoint_kernel(const uint8_t* __restrict__ img, int B, int H,
                                                                               int W, float* __restrict__ partials,
-                                                                              int rstrips, int cstrips) {
+                                                                              int rstrips, int cstrips, uint32_t two,
+                                                                              uint32_t neg2) {
   const int lane = threadIdx.x & 31;
   const int cs = kMulti ? blockIdx.x % cstrips : 0;
   const int rs = (blockIdx.x / cstrips) % rstrips;
@@ -599,6 +603,8 @@ __global__ void __launch_bounds__(kAdjWarps * 32, 3) filter_ws_adjoint_kernel(co
 
   AdjState<KIND> st;
   st.lane = lane;
+  st.two = two;
+  st.neg2 = neg2;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     st.M[i] = active ? kOnes : 0u; st.C[i] = active ? 0u : kOnes;   // lanes right of the image hold e = 1, w = 0
@@ -855,11 +861,11 @@ cudaError_t launch_filter_ws_adjoint(const void* img, int B, int H, int W, int k
   const uint8_t* im = static_cast<const uint8_t*>(img);
   const int grid = int(ctas), thr = kAdjWarps * 32;
   if (kind == PRED_KB) {
-    if (cstrips > 1) filter_ws_adjoint_kernel<PRED_KB, true><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips);
-    else filter_ws_adjoint_kernel<PRED_KB, false><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips);
+    if (cstrips > 1) filter_ws_adjoint_kernel<PRED_KB, true><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips, 2u, 0xfffffffeu);
+    else filter_ws_adjoint_kernel<PRED_KB, false><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips, 2u, 0xfffffffeu);
   } else {
-    if (cstrips > 1) filter_ws_adjoint_kernel<PRED_AVG, true><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips);
-    else filter_ws_adjoint_kernel<PRED_AVG, false><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips);
+    if (cstrips > 1) filter_ws_adjoint_kernel<PRED_AVG, true><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips, 2u, 0xfffffffeu);
+    else filter_ws_adjoint_kernel<PRED_AVG, false><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips, 2u, 0xfffffffeu);
   }
   return cudaGetLastError();
 }

@@ -182,21 +182,31 @@ def run_ours(args):
         est_sampler.start()
         est_imgs = imgs.repeat((n_est + per_gpu - 1) // per_gpu, 1, 1, 1)[:n_est].contiguous()
         est = {}
+        # nvidia-smi takes ~1 s to come up and holds driver locks while it does: launches stall behind it, which a
+        # 0.4 ms kernel shows. Warm up until its first sample has arrived, then time.
+        t_wait = time.perf_counter()
+        while not est_sampler.rows and time.perf_counter() - t_wait < 5.0:
+            W.ws_estimate(est_imgs, 'KB', weighted=0)
+            torch.cuda.synchronize()
         for weighted in (0, 1):
             for _ in range(10):   # also lets the clocks ramp before the timed repetitions
                 W.ws_estimate(est_imgs, 'KB', weighted=weighted)
             torch.cuda.synchronize()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            reps = 10
-            for _ in range(reps):
-                W.ws_estimate(est_imgs, 'KB', weighted=weighted)
-            a1.record()
-            torch.cuda.synchronize()
-            sec = a0.elapsed_time(a1) / reps / 1e3
+            groups, reps = [], 100   # long groups: the host runs ahead of the GPU and absorbs nvidia-smi polling stalls
+            for _ in range(3):
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(reps):
+                    W.ws_estimate(est_imgs, 'KB', weighted=weighted)
+                a1.record()
+                torch.cuda.synchronize()
+                groups.append(a0.elapsed_time(a1) / reps / 1e3)
+            sec = sorted(groups)[1]   # median of three groups of 100 back-to-back calls
             gbs = (S * S + 4) * n_est / sec / 1e9
             est[f'kb_w{weighted}'] = {'images_per_s': n_est / sec, 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                                       'frac': gbs / pk['hbm_gbs'], 'bound': 'hbm', 'images': n_est}
+                                       'frac': gbs / pk['hbm_gbs'], 'bound': 'hbm', 'images': n_est,
+                                       'kernel': 'filter_ws_adjoint_kernel + finalize_kernel' if weighted == 0
+                                       else 'filter_ws_fast_kernel + finalize_kernel'}
         del est_imgs
         est['clocks'] = est_sampler.stop()
         torch.cuda.empty_cache()
@@ -303,7 +313,7 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
                      'frac': achieved / pk['tf_sustained'], 'traffic': 0.922e9 * last_mb * (S / 512) ** 2, 'traffic_note': 'dram__bytes_read+write summed over the 11 launches of a 32-image pass from the ncu --set full capture in profiles/r01_ncu_halo_kernels.md (0.922 GB per 512x512 image), scaled to this pass', 'peak_source': pk['source'] + ' sustained bf16',
-                     'kernel': 'conv_mma_kernel (11 launches per micro-batch)', 'issued_tflops': 3 * achieved,
+                     'kernel': 'conv_halo_kernel / conv_halo2_kernel / upconv_res_kernel (11 tensor-core launches per micro-batch)', 'issued_tflops': 3 * achieved,
                      'issued_frac': 3 * achieved / pk['tf_sustained'],
                      'note': 'achieved = algorithmic 2*MACs of the 11 tensor-core layers / their summed CUDA-event time; '
                              'every MAC is issued as 3 bf16 MMAs (hi*hi, lo*hi, hi*lo), so issued = 3x algorithmic'},

@@ -98,6 +98,14 @@ int wsu_ws_from_prediction(int device, const void* img_dev, int img_dtype, const
                            const float* xbias_dev, int weighted, int clip, int crop, float* beta_dev, float* l1_dev, int B,
                            int H, int W, void* stream);
 
+/* Gradient of beta_hat with respect to the prediction, for the training losses WSLoss / L1WSLoss
+ * (src/_defs/losses.py:45-115): beta_hat_b = (1/n) sum_crop (x - x_bar)(x - scale*o) is linear in o, so
+ * grad_dev[b,p] = coef_dev[b] * (-scale) * (x_p - x_bar_p) / n inside the crop, 0 outside. coef_dev (B) float32 is
+ * dLoss/dbeta_hat_b from the caller's autograd; scale = 255 for outputs in [0,1], 1 for pixel units;
+ * grad_dev (B,1,H,W) float32. */
+int wsu_ws_grad_prediction(int device, const void* img_dev, int img_dtype, const float* coef_dev, int crop, float scale,
+                           float* grad_dev, int B, int H, int W, void* stream);
+
 /* ---- introspection for the per-layer parity tests: copy a feature map of the LAST micro-batch of the last forward
  * as float32 NCHW (hi+lo recombined). name in {"e11","e12","p1","e21",...,"u3","d31","d32",...}. with_halo=1 returns
  * (B,C,H+2,W+2) including the materialised reflect border. dims_out receives (B,C,H,W) of the returned tensor. */

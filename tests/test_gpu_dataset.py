@@ -84,3 +84,35 @@ def test_roc_from_gpu_beta_hat(cuda_dev):
                        'beta_hat': np.concatenate([bc, bs])})
     roc = produce_roc(df)
     assert roc['auc'].iloc[0] > 0.95 and roc['p_e'].iloc[0] < 0.1
+
+
+def test_ws_losses_backward_matches_torch_autograd(cuda_dev):
+    """WSLoss / L1WSLoss (src/_defs/losses.py:45-115) are differentiable in the predictor output: the gradient from
+    wsu_ws_grad_prediction must equal torch autograd applied to the reference's own formula."""
+    from ws_unet_b200.metrics import L1WSLoss, WSLoss
+    g = torch.Generator().manual_seed(3)
+    B, H, Wd = 5, 24, 40
+    inputs = (torch.randint(0, 256, (B, 1, H, Wd), generator=g).float() / 255.).to(cuda_dev)
+    covers = (torch.randint(0, 256, (B, 1, H, Wd), generator=g).float() / 255.).to(cuda_dev)
+    alphas = torch.tensor([0.0, 0.1, 0.4, 1.0, 0.2], device=cuda_dev)
+    base = (inputs + 0.02 * torch.randn(B, 1, H, Wd, generator=g).to(cuda_dev)).clamp(0, 1)
+    sgn = 2. * (torch.round(inputs[1] * 255.).int() & 1).float() - 1.
+    base[1] = inputs[1] + 0.3 * sgn / 255.      # beta_hat = -0.3 on this image: relu gate closed, WS gradient 0 there
+
+    def ref_ws(outputs):                        # losses.py:46-89 verbatim in torch ops
+        x, o = inputs * 255., outputs * 255.
+        xbar = (torch.round(x).int() ^ 1).float()
+        w = torch.ones_like(x) / (torch.numel(x) / float(x.size(0)))
+        bh = torch.relu(torch.sum(w * (x - xbar) * (x - o), dim=(1, 2, 3)))
+        return torch.mean(torch.abs(bh - alphas / 2.))
+
+    for ours, ref in ((WSLoss(), ref_ws), (L1WSLoss(), lambda o: torch.mean(torch.abs(covers - o)) + ref_ws(o))):
+        o1 = base.clone().requires_grad_(True)
+        o2 = base.clone().requires_grad_(True)
+        l1 = ours(o1, (covers, alphas), inputs)
+        l2 = ref(o2)
+        l1.backward()
+        l2.backward()
+        assert abs(l1.item() - l2.item()) < 1e-5
+        assert torch.allclose(o1.grad, o2.grad, rtol=1e-5, atol=1e-9)
+        assert o1.grad[2].abs().max() > 0 and o1.grad[1].abs().max() == (0 if isinstance(ours, WSLoss) else o1.grad[1].abs().max())

@@ -866,6 +866,18 @@ int wsu_filter_ws_estimate_host(int device, const uint8_t* img_host, int kind, i
   return WSU_OK;
 }
 
+int wsu_ws_grad_prediction(int device, const void* img_dev, int img_dtype, const float* coef_dev, int crop, float scale,
+                           float* grad_dev, int B, int H, int W, void* stream) {
+  if (!img_dev || !coef_dev || !grad_dev) return fail(WSU_ERR_INVALID, "null tensor pointer");
+  if (img_dtype != WSU_U8 && img_dtype != WSU_F32) return fail(WSU_ERR_INVALID, "dtype must be WSU_U8 or WSU_F32");
+  if (crop < 0 || crop > 1) return fail(WSU_ERR_INVALID, "crop must be 0 or 1");
+  if (B <= 0 || B > 65535 || H < 1 + 2 * crop || W < 1 + 2 * crop) return fail(WSU_ERR_INVALID, "need 1 <= B <= 65535 and a non-empty crop");
+  CUDA_TRY(cudaSetDevice(device));
+  LAUNCH_TRY(launch_ws_grad_pred(img_dev, img_dtype == WSU_F32, coef_dev, grad_dev, B, H, W, crop, scale,
+                                 static_cast<cudaStream_t>(stream)));
+  return WSU_OK;
+}
+
 int wsu_ws_from_prediction(int device, const void* img_dev, int img_dtype, const float* xhat_dev, int xhat_cropped,
                            const float* xbias_dev, int weighted, int clip, int crop, float* beta_dev, float* l1_dev, int B,
                            int H, int W, void* stream) {

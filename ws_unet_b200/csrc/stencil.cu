@@ -9,6 +9,7 @@
 //                           external predictor output).
 //   * finalize_kernel     - deterministic fixed-order reduction of the partial sums to beta_hat / l1 per image.
 //   * pack / unpack       - NCHW fp32 <-> split-bf16 NHWC, used by the per-layer parity tests.
+#include <algorithm>
 #include "stencil.h"
 #include "ws_math.cuh"
 
@@ -730,6 +731,27 @@ __global__ void __launch_bounds__(256) ws_from_pred_kernel(const void* __restric
   }
 }
 
+// ------------------------------------------------------------------------------------------------ WS loss gradient
+// beta_hat_b = (1/n) sum_{p in crop} (x_p - x_bar_p)(x_p - scale * o_p)  (WSLoss._error, src/_defs/losses.py:46-61, with
+// scale = 255 for outputs in [0,1]) is linear in the prediction o: d beta_hat_b / d o_p = -scale (x_p - x_bar_p) / n.
+// grad[b,p] = coef[b] * that inside the crop and 0 outside; coef[b] = dL/d beta_hat_b comes from the caller's autograd.
+template <bool kFloatIn>
+__global__ void __launch_bounds__(256) ws_grad_pred_kernel(const void* __restrict__ img, const float* __restrict__ coef,
+                                                           float* __restrict__ grad, int H, int W, int crop, float scale,
+                                                           float inv_n) {
+  const int b = blockIdx.y;
+  const float c = -coef[b] * scale * inv_n;
+  const size_t px = size_t(H) * W;
+  for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < px; i += size_t(gridDim.x) * 256) {
+    const int y = int(i / W), x = int(i - size_t(y) * W);
+    float xv, xbar;
+    if (kFloatIn) ws_load_f32(static_cast<const float*>(img)[b * px + i], xv, xbar);
+    else ws_load_u8(static_cast<const uint8_t*>(img)[b * px + i], xv, xbar);
+    const bool in = (y >= crop) && (y < H - crop) && (x >= crop) && (x < W - crop);
+    grad[b * px + i] = in ? c * (xv - xbar) : 0.f;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ finalize
 // One warp per image; partial records are summed in double in a fixed order => beta_hat is bit-reproducible
 // across runs, batch composition and GPU count.
@@ -908,6 +930,16 @@ cudaError_t launch_ws_from_pred(const void* img, int img_is_float, const float* 
   else
     ws_from_pred_kernel<false><<<B * chunks, 256, 0, stream>>>(img, xhat, xhat_cropped, xbias, B, H, W, weighted, crop,
                                                                partials, chunks);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ws_grad_pred(const void* img, int img_is_float, const float* coef, float* grad, int B, int H, int W,
+                                int crop, float scale, cudaStream_t stream) {
+  const size_t px = size_t(H) * W;
+  const dim3 grid(unsigned(std::min<size_t>((px + 255) / 256, 1024)), unsigned(B));
+  const float inv_n = 1.f / (float(H - 2 * crop) * float(W - 2 * crop));
+  if (img_is_float) ws_grad_pred_kernel<true><<<grid, 256, 0, stream>>>(img, coef, grad, H, W, crop, scale, inv_n);
+  else ws_grad_pred_kernel<false><<<grid, 256, 0, stream>>>(img, coef, grad, H, W, crop, scale, inv_n);
   return cudaGetLastError();
 }
 

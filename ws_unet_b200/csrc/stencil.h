@@ -25,6 +25,8 @@ cudaError_t launch_filter_ws(const void* img, int img_is_float, int B, int H, in
 cudaError_t launch_ws_from_pred(const void* img, int img_is_float, const float* xhat, int xhat_cropped, const float* xbias,
                                 int B, int H, int W, int weighted, int crop, float* partials, int chunks,
                                 cudaStream_t stream);
+cudaError_t launch_ws_grad_pred(const void* img, int img_is_float, const float* coef, float* grad, int B, int H, int W,
+                                int crop, float scale, cudaStream_t stream);
 cudaError_t launch_finalize(const float* partials, int records, int B, float npix, int clip, int correct_bias,
                             float* beta_hat, float* l1, cudaStream_t stream);
 cudaError_t launch_pack(const float* src, Act dst, cudaStream_t stream);

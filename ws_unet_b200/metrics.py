@@ -1,5 +1,7 @@
 """Consumers of the beta_hat vector and the batched training-side definitions, mirrored from the reference:
-  * WSLoss / WSMeter  - src/_defs/losses.py:45-89, src/_defs/metrics.py:116-142 (forward values only; no autograd)
+  * WSLoss / L1WSLoss / WSMeter - src/_defs/losses.py:27-115, src/_defs/metrics.py:116-142; the losses are differentiable
+    with respect to the predictor output (beta_hat is linear in it: wsu_ws_grad_prediction), so they can drive an
+    autograd graph that ends in a torch predictor
   * produce_roc       - src/ws/roc.py:198-283 (501-threshold ROC, AUC, P_E from beta_hat)
 The WS arithmetic runs through libwsunet (wsu_ws_from_prediction); ROC is a few thousand scalar ops on the host.
 """
@@ -9,17 +11,53 @@ import numpy as np
 import pandas as pd
 import torch
 
-from . import ws
+import ctypes
+
+from . import _native, ws
+
+
+class _WSBetas(torch.autograd.Function):
+    """beta_hat (unclipped) of a batch as a differentiable function of the predictor output in [0,1]."""
+
+    @staticmethod
+    def forward(ctx, outputs, inputs, crop):
+        ctx.save_for_backward(inputs)
+        ctx.crop = int(crop)
+        ctx.out_shape = outputs.shape
+        return ws.ws_from_prediction(inputs, outputs.detach().reshape(outputs.shape[0], *outputs.shape[-2:]) * 255.,
+                                     weighted=0, clip=False, crop=int(crop))
+
+    @staticmethod
+    def backward(ctx, grad_beta):
+        (inputs,) = ctx.saved_tensors
+        images, dtype = ws._prep_images(inputs)
+        B, _, H, W = images.shape
+        dev = images.device
+        coef = grad_beta.to(torch.float32).contiguous()
+        grad = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(_native.load().wsu_ws_grad_prediction(
+                dev.index, ctypes.c_void_p(images.data_ptr()), dtype, ctypes.c_void_p(coef.data_ptr()), ctx.crop, 255.,
+                ctypes.c_void_p(grad.data_ptr()), B, H, W, _native.stream_ptr(dev)), 'wsu_ws_grad_prediction')
+        return grad.reshape(ctx.out_shape), None, None
 
 
 def ws_betas_hat(outputs: torch.Tensor, inputs: torch.Tensor, crop: int = 0) -> torch.Tensor:
     """betas_hat of WSLoss._error (crop=0, relu; losses.py:46-61) or WSMeter.update (crop=1, clip; metrics.py:122-137):
-    images (B,1,H,W) float32 in [0,1] on a CUDA device; outputs = predictor output in [0,1]."""
-    return ws.ws_from_prediction(inputs, outputs[:, 0] * 255., weighted=0, clip=True, crop=crop)
+    images (B,1,H,W) float32 in [0,1] on a CUDA device; outputs = predictor output in [0,1]. Differentiable in outputs."""
+    return torch.relu(_WSBetas.apply(outputs, inputs, crop))
+
+
+class L1Loss:
+    """src/_defs/losses.py:27-36: mean |cover - output|."""
+
+    def __call__(self, outputs, targets, *args, **kw):
+        covers, _ = targets
+        return torch.mean(torch.abs(covers - outputs))
 
 
 class WSLoss:
-    """Forward value of src/_defs/losses.py:45-89: mean |relu(beta_hat) - alpha/2| over the batch."""
+    """src/_defs/losses.py:45-89: mean |relu(beta_hat) - alpha/2| over the batch (whole image, uniform weights)."""
 
     def _error(self, outputs, inputs, betas):
         return torch.abs(ws_betas_hat(outputs, inputs, crop=0) - betas.to(outputs.device))
@@ -27,6 +65,16 @@ class WSLoss:
     def __call__(self, outputs, targets, inputs):
         _, alphas = targets
         return torch.mean(self._error(outputs, inputs, alphas / 2.))
+
+
+class L1WSLoss:
+    """src/_defs/losses.py:92-115: prediction MAE + WS MAE."""
+
+    def __init__(self):
+        self.l1_loss, self.ws_loss = L1Loss(), WSLoss()
+
+    def __call__(self, outputs, targets, inputs):
+        return self.l1_loss(outputs, targets) + self.ws_loss(outputs, targets, inputs)
 
 
 class WSMeter:

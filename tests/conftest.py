@@ -30,6 +30,11 @@ def data_golden():
 
 
 @pytest.fixture(scope='session')
+def defs_golden():
+    return dict(np.load(GOLDEN / 'defs_golden.npz'))
+
+
+@pytest.fixture(scope='session')
 def cuda_dev():
     import torch
     if not torch.cuda.is_available():

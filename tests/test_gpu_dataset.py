@@ -116,3 +116,30 @@ def test_ws_losses_backward_matches_torch_autograd(cuda_dev):
         assert abs(l1.item() - l2.item()) < 1e-5
         assert torch.allclose(o1.grad, o2.grad, rtol=1e-5, atol=1e-9)
         assert o1.grad[2].abs().max() > 0 and o1.grad[1].abs().max() == (0 if isinstance(ours, WSLoss) else o1.grad[1].abs().max())
+
+
+def test_filter_residuals_match_reference_golden(cuda_dev, ws_golden, defs_golden):
+    """get_filter_residuals (matrix form, float64) with the reference's argument list, and the
+    batched stencil-kernel residual map, both equal the reference's residuals exactly on 8-bit pixels; the MAE of
+    results/prediction/filters.csv is their mean absolute value (also what ws_estimate(..., return_l1=True) returns)."""
+    import ws_unet_b200 as W
+    from ws_unet_b200 import defs, filters
+    proc = defs.get_processor(channels=(3,))
+    for tag in ('cover', 'lsbr04'):
+        img = ws_golden[f'img_{tag}']
+        x4 = np.repeat(img[..., None], 4, axis=2)
+        d = torch.from_numpy(img)[None, None].to(cuda_dev)
+        for name in ('KB', 'AVG'):
+            ref = defs_golden[f'resid_{tag}_{name}']
+            got = filters.get_filter_residuals('mem', filter=filters.NAMED_FILTERS[name], process_image=proc, imread=lambda f: x4)
+            assert got.dtype == np.float64 and got.shape == ref.shape and np.array_equal(got, ref)
+            stencil = filters.filter_residuals(d, name)[0].cpu().numpy()
+            assert np.array_equal(stencil.reshape(-1, 1), ref)
+            mae = defs_golden[f'mae_{tag}_{name}'][0]
+            assert abs(np.abs(got).mean() - mae) < 1e-12
+            _, l1 = W.ws_estimate(d, name, weighted=0, return_l1=True)
+            assert abs(l1.item() - mae) < 1e-4
+    x4 = np.repeat(ws_golden['img_cover'][..., None], 4, axis=2)
+    got = filters.get_filter_residuals('mem', filter=defs_golden['coef_ols'], imread=lambda f: x4,
+                                       process_image=defs.get_processor(channels=(3,), inbayer='01'))
+    assert np.abs(got - defs_golden['resid_cover_ols']).max() < 1e-10     # fitted vector: float64 matvec, order of sums differs

@@ -106,3 +106,25 @@ def test_sharded_gather_world2_gloo(n):
     expect = ((torch.arange(n, dtype=torch.float32) * 0.5 + 1) * 2).tolist()
     for _, got in res:
         assert got == expect
+
+
+def test_processors_and_image_readers_match_reference_golden(defs_golden):
+    """get_processor (N x 9 neighbour matrix, every inbayer lattice), get_processor_2d and the
+    imread helpers reproduce the reference's outputs (tests/golden/make_golden_defs.py) exactly."""
+    from ws_unet_b200 import defs
+    img = defs_golden['proc_img']
+    for inb in (None, '00', '01', '10', '11'):
+        got = defs.get_processor(channels=(3,), inbayer=inb)(img)
+        ref = defs_golden[f'proc_{inb}']
+        assert got.shape == ref.shape and got.dtype == ref.dtype and np.array_equal(got, ref), inb
+    for key, ch in (('proc2d_3', (3,)), ('proc2d_02', (0, 2))):
+        got = defs.get_processor_2d(channels=ch)(img)
+        assert got.dtype == np.float32 and np.array_equal(got, defs_golden[key])
+    png = pathlib.Path(__file__).parent / 'golden' / 'rgb_9x11.png'
+    x4 = defs.imread4_u8(png)
+    assert x4.dtype == np.uint8 and np.array_equal(x4, defs_golden['imread4_rgb'])
+    assert np.array_equal(defs.imread_u8(png), defs_golden['imread_u8_rgb'])
+    assert defs.imread4_f32(png).dtype == np.float32 and defs.imread_f32(png).dtype == np.float32
+    # the target column of the matrix is the interior of the image, the first column its top-left neighbours
+    mat = defs.get_processor(channels=(3,))(img)
+    assert np.array_equal(mat[:, 8], img[1:-1, 1:-1, 3].reshape(-1)) and np.array_equal(mat[:, 0], img[:-2, :-2, 3].reshape(-1))

@@ -7,6 +7,7 @@
 from __future__ import annotations
 
 import ctypes
+import typing
 
 import numpy as np
 import torch
@@ -58,6 +59,34 @@ def filter_predict(images: torch.Tensor, filter_name: str) -> torch.Tensor:
     return out
 
 
+def filter_residuals(images: torch.Tensor, filter_name: str) -> torch.Tensor:
+    """Batched residual map y - y_hat in float64, (B,H-2,W-2): what get_filter_residuals returns per image, reshaped.
+    For uint8 pixels the KB/AVG prediction is an integer multiple of 1/4 (1/8) and exact in float32, so the float64
+    residual is exact."""
+    if images.dim() == 4:
+        images = images[:, 0]
+    pred = filter_predict(images, filter_name).to(torch.float64)
+    centre = images[:, 1:-1, 1:-1]
+    centre = centre.to(torch.float64) if images.dtype == torch.uint8 else centre.to(torch.float64) * 255.
+    return centre - pred
+
+
+def get_filter_residuals(fname: str, filter: np.ndarray, process_image: typing.Callable, imread: typing.Callable = None,
+                         device=None, **kw) -> np.ndarray:
+    """src/filters/evaluate.py:53-76: residual of the linear predictor `filter` (8 x 1, float64) over the neighbour
+    matrix `process_image(imread(fname))` (N x 9, last column = target) -> (N, 1) float64. Any coefficient vector is
+    allowed (this is the OLS-fit path, not the per-image hot path): one float64 matrix-vector product on the GPU.
+    For the named KB / AVG vectors on 8-bit pixels every term is a multiple of 1/8 below 2^11, so the float64 result
+    is exact and equals `filter_residuals(image, name)` (the stencil kernel) element for element."""
+    from . import defs
+    dev = _device(device)
+    mat = np.asarray(process_image((imread or defs.imread4_u8)(fname)))
+    xt = torch.from_numpy(np.ascontiguousarray(mat[..., :-1], dtype=np.float64)).to(dev)
+    yt = torch.from_numpy(np.ascontiguousarray(mat[..., -1:], dtype=np.float64)).to(dev)
+    coef = torch.from_numpy(np.ascontiguousarray(filter, dtype=np.float64)).to(dev)
+    return (yt - xt @ coef).cpu().numpy()
+
+
 def infere_single(x: np.ndarray, filter_name: str, device=None) -> np.ndarray:
     """src/filters/evaluate.py:136-141: (H,W,C) float32 pixel units -> (H-2,W-2,1). Non-integer inputs (e.g. the
     +-1 difference image of estimate.py:127) go through the float path: the kernel sees x/255 like the reference."""
@@ -71,7 +100,9 @@ def infere_single(x: np.ndarray, filter_name: str, device=None) -> np.ndarray:
 def get_filter_estimator(filter_name: str, flatten: bool = False, device=None):
     """src/filters/evaluate.py:144-146."""
     if flatten:
-        raise NotImplementedError("flatten=True is the matrix-form OLS path (filters/evaluate.py:53-76), not the hot path")
+        raise NotImplementedError("flatten=True hands the 8x1 OLS vector to a 2-D convolution in the reference "
+                                  "(filters/evaluate.py:136-146), which is not a pixel predictor; the matrix form is "
+                                  "get_filter_residuals")
     if filter_name not in NAMED_FILTERS_2D:
         raise KeyError(filter_name)
     return lambda x: infere_single(x, filter_name, device)

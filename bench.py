@@ -206,7 +206,7 @@ def run_ours(args):
             est[f'kb_w{weighted}'] = {'images_per_s': n_est / sec, 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
                                        'frac': gbs / pk['hbm_gbs'], 'bound': 'hbm', 'images': n_est,
                                        'kernel': 'filter_ws_adjoint_kernel + finalize_kernel' if weighted == 0
-                                       else 'filter_ws_fast_kernel + finalize_kernel'}
+                                       else 'filter_ws_window_kernel + finalize_kernel'}
         del est_imgs
         est['clocks'] = est_sampler.stop()
         torch.cuda.empty_cache()

@@ -815,10 +815,16 @@ int wsu_filter_ws_estimate(int device, const void* img_dev, int img_dtype, int k
   // WSU_EST_KERNEL=packed keeps the 16-bit-lane kernel for A/B runs; default is the adjoint (parity-plane) kernel
   static const bool prefer_packed = [] { const char* e = std::getenv("WSU_EST_KERNEL"); return e && !std::strcmp(e, "packed"); }();
   const bool adjoint = packed && !prefer_packed && filter_ws_adjoint_ok(img_dev, H, W);
-  if (fast) records = adjoint ? filter_ws_adjoint_records(H, W) : packed ? filter_ws_packed_records(H, W) : filter_ws_fast_records(H, W);
+  // weighted and/or L1-reporting requests: dp4a window kernel (WSU_EST_KERNEL=fast keeps the scalar sliding-window kernel)
+  static const bool prefer_fast = [] { const char* e = std::getenv("WSU_EST_KERNEL"); return e && !std::strcmp(e, "fast"); }();
+  const bool window = fast && !packed && !prefer_fast && !prefer_packed && filter_ws_window_ok(img_dev, H, W);
+  if (fast) records = adjoint ? filter_ws_adjoint_records(H, W) : packed ? filter_ws_packed_records(H, W)
+                    : window ? filter_ws_window_records(H, W) : filter_ws_fast_records(H, W);
   CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&partials), size_t(B) * records * kPartialSlots * 4, st));
   if (adjoint)
     LAUNCH_TRY(launch_filter_ws_adjoint(img_dev, B, H, W, kind, partials, st));
+  else if (window)
+    LAUNCH_TRY(launch_filter_ws_window(img_dev, B, H, W, kind, weighted, l1_dev != nullptr, partials, st));
   else if (packed)
     LAUNCH_TRY(launch_filter_ws_packed(img_dev, B, H, W, kind, partials, st));
   else if (fast)

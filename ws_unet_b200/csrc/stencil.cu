@@ -664,6 +664,150 @@ __global__ void __launch_bounds__(kAdjWarps * 32, 3) filter_ws_adjoint_kernel(co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ window (dp4a) filter WS
+// Local-variance weighted (and / or L1-reporting) KB / AVG estimator. Same task shape as the adjoint kernel (a warp walks
+// a 512-pixel-wide strip, 16 pixels per lane and row, neighbours through shuffles), but the per-pixel weights force
+// per-pixel arithmetic. Every pixel's 3-byte row window (left, centre, right) sits in one 32-bit register, so each of
+// the nine-point sums is three chained dp4a: S9 = sum x (coefficients 1,1,1), Q9 = sum x^2 (window against itself),
+// R = D(x - x_hat) (KB: rows (1,-2,1), (-2,4,-2), (1,-2,1); AVG: 8x - S8). Then
+//   -64 (5 + var) = S8^2 - 8 Q8 - 320  (exact integer, |.| < 2^23), S8 = S9 - x, Q8 = Q9 - x^2,
+// and the weight is its reciprocal (MUFU.RCP, 1 ulp: the reference's own float32 weights are only good to 0.5 %,
+// SURVEY.md 8c). Weights are carried with the opposite sign (no negation needed); the sign cancels in sum(w r)/sum(w).
+// The parity sign is applied by accumulating all pixels and the odd pixels separately: sum s*R = 2 sum_odd - sum_all.
+constexpr int kWinRows = 64;   // output rows per warp task
+constexpr int kWinWarps = 8;
+
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b_s8x4, int c) {   // unsigned bytes of a times signed bytes of b
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b_s8x4), "r"(c));
+  return d;
+}
+
+template <int KIND, int WEIGHTED, bool kL1, bool kMulti>
+__global__ void __launch_bounds__(kWinWarps * 32, 2) filter_ws_window_kernel(const uint8_t* __restrict__ img, int B, int H,
+                                                                             int W, float* __restrict__ partials,
+                                                                             int rstrips, int cstrips) {
+  const int lane = threadIdx.x & 31;
+  const int cs = kMulti ? blockIdx.x % cstrips : 0;
+  const int rs = (blockIdx.x / cstrips) % rstrips;
+  const int b = (blockIdx.x / (cstrips * rstrips)) * kWinWarps + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int x = cs * 512 + lane * 16;
+  const bool active = x < W;
+  const int r0 = 1 + rs * kWinRows, r1 = min(r0 + kWinRows, H - 1);   // interior rows [r0, r1) of this task
+  const bool first_col = active && x == 0, last_col = active && (x + 16 == W);
+  const bool edge_l = kMulti && (lane == 0) && active && x > 0;
+  const bool edge_r = kMulti && (lane == 31) && active && (x + 16 < W);
+  const int edge_off = edge_l ? -4 : 16;
+
+  // masked 3-byte windows (left, centre, right, 0) of the 16 pixels of a row
+  auto windows = [&](const uint4& v, uint32_t ex, uint32_t (&win)[16]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t wl = __shfl_up_sync(0xffffffffu, w[3], 1), wr = __shfl_down_sync(0xffffffffu, w[0], 1);
+    if (kMulti) {
+      if (lane == 0) wl = ex;
+      if (lane == 31) wr = ex;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t prev = i ? w[i - 1] : wl, next = i < 3 ? w[i + 1] : wr;
+      win[4 * i + 0] = __funnelshift_r(prev, w[i], 24) & 0x00ffffffu;
+      win[4 * i + 1] = w[i] & 0x00ffffffu;
+      win[4 * i + 2] = w[i] >> 8;
+      win[4 * i + 3] = __funnelshift_r(w[i], next, 16) & 0x00ffffffu;
+    }
+  };
+  const uint8_t* rp = img + size_t(b) * H * W + size_t(r0 - 1) * W + (active ? x : 0);
+  auto fetch = [&](uint4& v, uint32_t& ex) {
+    v = active ? __ldg(reinterpret_cast<const uint4*>(rp)) : make_uint4(0u, 0u, 0u, 0u);
+    ex = 0u;
+    if (kMulti && (edge_l || edge_r)) ex = __ldg(reinterpret_cast<const uint32_t*>(rp + edge_off));
+    rp += W;
+  };
+
+  uint32_t ra[16], rb[16], rc[16];   // three row buffers; their roles (top, mid, bottom) rotate statically
+  {
+    uint4 v0, v1;
+    uint32_t e0, e1;
+    fetch(v0, e0);
+    fetch(v1, e1);
+    windows(v0, e0, ra);
+    windows(v1, e1, rb);
+  }
+  int acc_all = 0, acc_odd = 0, acc_l1 = 0;
+  float f_all = 0.f, f_odd = 0.f, f_w = 0.f;
+  constexpr int kOnes3 = 0x00010101;
+  constexpr int kEdgeRow = 0x0001fe01;    // ( 1, -2,  1, 0)
+  constexpr int kMidRow = 0x00fe04fe;     // (-2,  4, -2, 0)
+
+  uint4 vnext;
+  uint32_t enext;
+  fetch(vnext, enext);
+  int y = r0;
+  // one interior row: `bot` receives the windows of row y+1, then the 16 pixels of row y are accumulated
+  auto row = [&](const uint32_t (&top)[16], const uint32_t (&mid)[16], uint32_t (&bot)[16]) {
+    windows(vnext, enext, bot);
+    if (y + 1 < r1) fetch(vnext, enext);   // the next row's load overlaps this row's arithmetic
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      // columns 0 and W-1 are not estimated: their residual / weight is forced to 0 (only pixels 0 and 15 can be affected)
+      const bool dead = (j == 0 && first_col) || (j == 15 && last_col);
+      const int c = int(__byte_perm(mid[j], 0u, 0x4441));
+      int R, s9 = 0;
+      if (KIND == PRED_AVG || WEIGHTED != WS_UNWEIGHTED)
+        s9 = dp4a_us(bot[j], kOnes3, dp4a_us(mid[j], kOnes3, dp4a_us(top[j], kOnes3, 0)));
+      if (KIND == PRED_KB) R = dp4a_us(bot[j], kEdgeRow, dp4a_us(mid[j], kMidRow, dp4a_us(top[j], kEdgeRow, 0)));
+      else R = 9 * c - s9;
+      if ((j == 0 || j == 15) && dead) R = 0;
+      if (WEIGHTED != WS_UNWEIGHTED) {
+        const uint32_t q9 = __dp4a(bot[j], bot[j], __dp4a(mid[j], mid[j], __dp4a(top[j], top[j], 0u)));
+        const int s8 = s9 - c;
+        const int q8 = int(q9) - c * c;
+        const int nd = s8 * s8 - 8 * q8 - 320;              // -64 (5 + var)
+        const float fd = __int2float_rn(nd);
+        float wgt = fd;
+        if (WEIGHTED == WS_WEIGHTED) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(wgt) : "f"(fd));
+        if ((j == 0 || j == 15) && dead) wgt = 0.f;
+        const float fr = __int2float_rn(R);
+        f_all = fmaf(wgt, fr, f_all);
+        if (c & 1) f_odd = fmaf(wgt, fr, f_odd);
+        f_w += wgt;
+      } else {
+        acc_all += R;
+        acc_odd += R * (c & 1);
+      }
+      if (kL1) acc_l1 += abs(R);
+    }
+    ++y;
+  };
+  while (y < r1) {
+    row(ra, rb, rc);
+    if (y < r1) row(rb, rc, ra);
+    if (y < r1) row(rc, ra, rb);
+  }
+  if (!active) { acc_all = acc_odd = acc_l1 = 0; f_all = f_odd = f_w = 0.f; }   // lanes right of the image saw zeros
+
+  constexpr float kScale = (KIND == PRED_KB) ? 0.25f : 0.125f;
+  const int rows = max(r1 - r0, 0);
+  const int npx_lane = active ? rows * (16 - int(first_col) - int(last_col)) : 0;
+  const int sr = __reduce_add_sync(0xffffffffu, 2 * acc_odd - acc_all);
+  const int sl = __reduce_add_sync(0xffffffffu, acc_l1);
+  const int sn = __reduce_add_sync(0xffffffffu, npx_lane);
+  const float fr = warp_sum(2.f * f_odd - f_all), fw = warp_sum(f_w);
+  if (lane == 0) {
+    float* dst = partials + ((size_t(b) * rstrips + rs) * cstrips + cs) * 2 * kPartialSlots;
+    const int sr_lo = sr & 0xfff, sl_lo = sl & 0xfff;
+    dst[0] = WEIGHTED ? fr * kScale : float(sr - sr_lo) * kScale;
+    dst[1] = WEIGHTED ? fw : float(sn);
+    dst[2] = float(sl - sl_lo) * kScale;
+    dst[3] = 0.f;
+    dst[4] = WEIGHTED ? 0.f : float(sr_lo) * kScale;
+    dst[5] = 0.f;
+    dst[6] = float(sl_lo) * kScale;
+    dst[7] = 0.f;
+  }
+}
+
 // WS terms against a caller-supplied prediction (pixel units), grid-stride per image chunk.
 template <bool kFloatIn>
 __global__ void __launch_bounds__(256) ws_from_pred_kernel(const void* __restrict__ img, const float* __restrict__ xhat,
@@ -889,6 +1033,42 @@ cudaError_t launch_filter_ws_adjoint(const void* img, int B, int H, int W, int k
     if (cstrips > 1) filter_ws_adjoint_kernel<PRED_AVG, true><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips, 2u, 0xfffffffeu);
     else filter_ws_adjoint_kernel<PRED_AVG, false><<<grid, thr, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips, 2u, 0xfffffffeu);
   }
+  return cudaGetLastError();
+}
+
+bool filter_ws_window_ok(const void* img, int H, int W) {
+  return (W % 16 == 0) && (reinterpret_cast<uintptr_t>(img) % 16 == 0) && H >= 3;
+}
+int filter_ws_window_records(int H, int W) { return ((H - 2 + kWinRows - 1) / kWinRows) * ((W + 511) / 512) * 2; }
+
+template <int KIND, int WEIGHTED, bool kL1>
+static void launch_window_t(const uint8_t* im, int B, int H, int W, float* partials, int rstrips, int cstrips, int grid,
+                            cudaStream_t stream) {
+  if (cstrips > 1)
+    filter_ws_window_kernel<KIND, WEIGHTED, kL1, true><<<grid, kWinWarps * 32, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips);
+  else
+    filter_ws_window_kernel<KIND, WEIGHTED, kL1, false><<<grid, kWinWarps * 32, 0, stream>>>(im, B, H, W, partials, rstrips, cstrips);
+}
+template <int KIND>
+static void launch_window_kind(const uint8_t* im, int B, int H, int W, int weighted, int want_l1, float* partials, int rstrips,
+                               int cstrips, int grid, cudaStream_t st) {
+  if (weighted == WS_UNWEIGHTED) launch_window_t<KIND, WS_UNWEIGHTED, true>(im, B, H, W, partials, rstrips, cstrips, grid, st);
+  else if (weighted == WS_WEIGHTED) {
+    if (want_l1) launch_window_t<KIND, WS_WEIGHTED, true>(im, B, H, W, partials, rstrips, cstrips, grid, st);
+    else launch_window_t<KIND, WS_WEIGHTED, false>(im, B, H, W, partials, rstrips, cstrips, grid, st);
+  } else {
+    if (want_l1) launch_window_t<KIND, WS_ANTIWEIGHTED, true>(im, B, H, W, partials, rstrips, cstrips, grid, st);
+    else launch_window_t<KIND, WS_ANTIWEIGHTED, false>(im, B, H, W, partials, rstrips, cstrips, grid, st);
+  }
+}
+cudaError_t launch_filter_ws_window(const void* img, int B, int H, int W, int kind, int weighted, int want_l1, float* partials,
+                                    cudaStream_t stream) {
+  const int rstrips = (H - 2 + kWinRows - 1) / kWinRows, cstrips = (W + 511) / 512;
+  const long long ctas = (long long)((B + kWinWarps - 1) / kWinWarps) * rstrips * cstrips;
+  if (ctas > 0x7fffffffll) return cudaErrorInvalidValue;
+  const uint8_t* im = static_cast<const uint8_t*>(img);
+  if (kind == PRED_KB) launch_window_kind<PRED_KB>(im, B, H, W, weighted, want_l1, partials, rstrips, cstrips, int(ctas), stream);
+  else launch_window_kind<PRED_AVG>(im, B, H, W, weighted, want_l1, partials, rstrips, cstrips, int(ctas), stream);
   return cudaGetLastError();
 }
 

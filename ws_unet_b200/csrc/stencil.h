@@ -20,6 +20,11 @@ cudaError_t launch_filter_ws_packed(const void* img, int B, int H, int W, int ki
 bool filter_ws_adjoint_ok(const void* img, int H, int W);
 int filter_ws_adjoint_records(int H, int W);
 cudaError_t launch_filter_ws_adjoint(const void* img, int B, int H, int W, int kind, float* partials, cudaStream_t stream);
+// window (dp4a) variant: weighted / anti-weighted and/or L1-reporting KB/AVG estimator on uint8 images, W % 16 == 0
+bool filter_ws_window_ok(const void* img, int H, int W);
+int filter_ws_window_records(int H, int W);
+cudaError_t launch_filter_ws_window(const void* img, int B, int H, int W, int kind, int weighted, int want_l1, float* partials,
+                                    cudaStream_t stream);
 cudaError_t launch_filter_ws(const void* img, int img_is_float, int B, int H, int W, int kind, int weighted, int want_bias,
                              float* xhat_out, float* partials, cudaStream_t stream);
 cudaError_t launch_ws_from_pred(const void* img, int img_is_float, const float* xhat, int xhat_cropped, const float* xbias,

@@ -175,7 +175,7 @@ def run_ours(args):
 
     # measured first, as its own workload, before the tensor-core chain heats the part up
     est = None
-    if rank == 0:
+    if rank == 0 and args.est_images > 0:
         # ---- estimator (HBM-bound, BASELINE.json configs[1]): KB-filter WS on resident uint8 images
         n_est = args.est_images
         est_sampler = ClockSampler(local)
@@ -337,7 +337,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--per-gpu', type=int, default=256, help='images per GPU per step')
     ap.add_argument('--micro-batch', type=int, default=0)
-    ap.add_argument('--est-images', type=int, default=10000, help='images of the KB-filter estimator measurement (configs[1])')
+    ap.add_argument('--est-images', type=int, default=10000, help='images of the KB-filter estimator measurement (configs[1]); 0 skips it (launch lists of the UNet step)')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--profile-images', type=int, default=32, help='images of the per-layer profiled pass')
     ap.add_argument('--size', type=int, default=512, help='image side; 1024 = BASELINE configs[4] (not the headline metric)')

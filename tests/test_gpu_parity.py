@@ -404,3 +404,18 @@ def test_host_buffer_entry_points(cuda_dev):
             assert torch.equal(W.ws_estimate_host(imgs, name, weighted=weighted), W.ws_estimate(imgs.to(cuda_dev), name, weighted=weighted).cpu())
     with pytest.raises(ValueError):
         W.ws_estimate_host(imgs.to(cuda_dev), 'KB')
+    # the handle's activation buffers are shared by the device-stream path and the host-buffer path (own streams):
+    # back-to-back calls without a sync in between must not overlap in them
+    m.set_micro_batch(2, cuda_dev)
+    dimgs = imgs.to(cuda_dev)
+    side = torch.cuda.Stream(device=cuda_dev)
+    for _ in range(4):
+        a = W.ws_estimate(dimgs, m, weighted=0, clip=False, return_l1=True)
+        b = W.ws_estimate_host(imgs, m, weighted=0, clip=False, return_l1=True)
+        with torch.cuda.stream(side):
+            c = W.ws_estimate(dimgs, m, weighted=0, clip=False, return_l1=True)
+        d = W.ws_estimate(dimgs, m, weighted=0, clip=False, return_l1=True)
+        torch.cuda.synchronize()
+        for r in (b, c, d):
+            assert torch.equal(a[0].cpu(), r[0].cpu()) and torch.equal(a[1].cpu(), r[1].cpu())
+    m.set_micro_batch(0, cuda_dev)

@@ -10,15 +10,15 @@ imgs = wdata.synthetic_stego_fast(n, 0.4, 512, 512, torch.device('cuda', 0), uni
 ref = None
 for name in ['KB', 'AVG']:
     for kw in [dict(weighted=0), dict(weighted=0, return_l1=True), dict(weighted=1)]:
-        for _ in range(3):
+        for _ in range(10):
             out = W.ws_estimate(imgs, name, **kw)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(5):
+        for _ in range(50):
             W.ws_estimate(imgs, name, **kw)
         e1.record()
         torch.cuda.synchronize()
-        s = e0.elapsed_time(e1) / 5 / 1e3
+        s = e0.elapsed_time(e1) / 50 / 1e3
         b = out[0] if isinstance(out, tuple) else out
         print(name, kw, f'{n / s / 1e6:.2f} M img/s  {262148 * n / s / 1e9:.0f} GB/s  {262148 * n / s / 1e9 / 6544:.3f} of HBM peak  beta[:3]={b[:3].tolist()}')

@@ -135,6 +135,12 @@ struct wsu_context {
   float* stage_out = nullptr;
   size_t stage_imgs = 0, stage_px = 0;
   cudaStream_t s_copy = nullptr, s_comp = nullptr;
+  // The activation buffers of the plan are shared by every call on this handle. Calls may arrive on different streams
+  // (torch's current stream, the host-buffer path's own compute stream): each call records ev_chain when it is done and
+  // a call on another stream waits for it first, so two passes never overlap in the buffers.
+  cudaEvent_t ev_chain = nullptr;
+  cudaStream_t chain_stream = nullptr;
+  bool chain_pending = false;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   // optional per-layer timing of the last micro-batch ("profile" option)
   bool profile = false;
@@ -147,6 +153,7 @@ struct wsu_context {
   // is off by default.
   bool fuse_e11 = false;
   int use_pair = 1;  // 3x3 layers as CTA pairs (tcgen05 cta_group::2): 0 never, 1 Cout>=128 layers (measured win), 2 all
+  int a_collector = 1;    // option "a_collector" (default on, +0.4 % measured): Cout >= 128 layers reuse A_hi from the A collector (hi*hi, hi*lo, lo*hi order)
   int l2_prefetch = 0;    // halo kernels prefetch the next item's boxes into L2 (option "l2_prefetch"); measured 1 % slower
   bool use_upres = true;  // transposed convs through upconv_res_kernel (option "upconv_resident")
   bool use_halo = true;  // 3x3 layers through conv_halo_kernel (option "halo"; 0 = per-tap reload kernel, for A/B runs)
@@ -404,6 +411,7 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
     const int n_tile = pl.convs[i].second.first, epi = pl.convs[i].second.second;
     const bool halo = h->use_halo && p.ntaps == 9;
     p.l2_prefetch = h->l2_prefetch;
+    p.a_collector = h->a_collector;
     if (nimg != pl.mb) {
       p.B = nimg;
       p.total_tiles = nimg * p.tiles_y * p.tiles_x * p.n_tiles * p.npos;
@@ -456,10 +464,19 @@ int unet_ws_device(wsu_context* h, const void* img, int dtype, int B, int H, int
     if (crop && (H < 3 || W < 3)) return fail(WSU_ERR_INVALID, "crop=1 needs H, W >= 3");
   }
   CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->ev_chain) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chain, cudaEventDisableTiming));
+  if (h->chain_pending && h->chain_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chain, 0));
   const int mb = pick_micro_batch(h, B, H, W);
   if ((rc = build_plan(h, mb, H, W))) return rc;
   const size_t px = size_t(H) * W;
   const size_t esz = dtype == WSU_F32 ? 4 : 1;
+  struct ChainDone {   // records the end of this call's work on every exit path
+    wsu_context* h;
+    cudaStream_t st;
+    ~ChainDone() {
+      if (cudaEventRecord(h->ev_chain, st) == cudaSuccess) { h->chain_stream = st; h->chain_pending = true; }
+    }
+  } chain_done{h, st};
   for (int b0 = 0; b0 < B; b0 += mb) {
     const int nimg = std::min(mb, B - b0);
     const uint8_t* im = static_cast<const uint8_t*>(img) + size_t(b0) * h->in_ch * px * esz;
@@ -524,6 +541,7 @@ int wsu_create(wsu_handle* out, int device, int nsteps, int in_channels, int out
   if (const char* e = std::getenv("WSU_CTA_PAIR")) h->use_pair = std::atoi(e);
   if (const char* e = std::getenv("WSU_FUSE_E11")) h->fuse_e11 = std::atoi(e) != 0;
   if (const char* e = std::getenv("WSU_HALO")) h->use_halo = std::atoi(e) != 0;
+  if (const char* e = std::getenv("WSU_A_COLLECTOR")) h->a_collector = std::atoi(e) != 0;
   *out = h;
   return WSU_OK;
 }
@@ -545,6 +563,7 @@ int wsu_destroy(wsu_handle h) {
   for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
   if (h->s_copy) cudaStreamDestroy(h->s_copy);
   if (h->s_comp) cudaStreamDestroy(h->s_comp);
+  if (h->ev_chain) cudaEventDestroy(h->ev_chain);
   delete h;
   return WSU_OK;
 }
@@ -558,6 +577,10 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
   }
   if (!std::strcmp(key, "fuse_e11")) {
     h->fuse_e11 = value != 0;
+    return WSU_OK;
+  }
+  if (!std::strcmp(key, "a_collector")) {
+    h->a_collector = value != 0;
     return WSU_OK;
   }
   if (!std::strcmp(key, "l2_prefetch")) {
@@ -942,7 +965,10 @@ int wsu_debug_layer(wsu_handle h, const char* name, float* dst_dev, size_t cap, 
   if (size_t(a.B) * a.C * Ho * Wo > cap) return fail(WSU_ERR_INVALID, "destination too small");
   if (dims_out) { dims_out[0] = a.B; dims_out[1] = a.C; dims_out[2] = Ho; dims_out[3] = Wo; }
   CUDA_TRY(cudaSetDevice(h->device));
-  LAUNCH_TRY(launch_unpack(a, dst_dev, with_halo, static_cast<cudaStream_t>(stream)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h->chain_pending && h->chain_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chain, 0));
+  LAUNCH_TRY(launch_unpack(a, dst_dev, with_halo, st));
+  if (cudaEventRecord(h->ev_chain, st) == cudaSuccess) { h->chain_stream = st; h->chain_pending = true; }  // the next pass must not overwrite what this copy reads
   return WSU_OK;
 }
 

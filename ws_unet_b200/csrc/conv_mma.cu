@@ -692,9 +692,15 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
                     const uint64_t da_lo = make_sw128_desc(a_lo + k * 32, kHaloSBO);
                     const uint64_t dw_hi = make_sw128_desc(w_hi + k * 32);
                     const uint64_t dw_lo = make_sw128_desc(w_lo + k * 32);
-                    umma_bf16(d, da_hi, dw_hi, idesc, (c | tap | k) != 0);
-                    umma_bf16(d, da_lo, dw_hi, idesc, 1);
-                    umma_bf16(d, da_hi, dw_lo, idesc, 1);
+                    if (p.a_collector) {   // A_hi read once for its two products
+                      umma_bf16_a_fill(d, da_hi, dw_hi, idesc, (c | tap | k) != 0);
+                      umma_bf16_a_lastuse(d, da_hi, dw_lo, idesc, 1);
+                      umma_bf16(d, da_lo, dw_hi, idesc, 1);
+                    } else {
+                      umma_bf16(d, da_hi, dw_hi, idesc, (c | tap | k) != 0);
+                      umma_bf16(d, da_lo, dw_hi, idesc, 1);
+                      umma_bf16(d, da_hi, dw_lo, idesc, 1);
+                    }
                   }
                   if (tap == 8) umma_commit(&a_empty[a_slot[j]]);
                 }
@@ -950,9 +956,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
                       umma_bf16_2sm(d, da_hi, dw_x, make_idesc_bf16_m(256, 128), (c | tap | k) != 0);  // Ahi * [Whi; Wlo]
                       umma_bf16_2sm(d, da_lo, dw_y, make_idesc_bf16_m(256, 64), 1);                    // Alo * Whi
                     } else {
-                      umma_bf16_2sm(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
-                      umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
-                      umma_bf16_2sm(d, da_hi, dw_y, idesc, 1);
+                      if (p.a_collector) {   // A_hi read once for its two products
+                        umma_bf16_2sm_a_fill(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
+                        umma_bf16_2sm_a_lastuse(d, da_hi, dw_y, idesc, 1);
+                        umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
+                      } else {
+                        umma_bf16_2sm(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
+                        umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
+                        umma_bf16_2sm(d, da_hi, dw_y, idesc, 1);
+                      }
                     }
                   }
                   if (tap == 8) umma_commit_2sm(&a_empty[a_slot[j]], 3);

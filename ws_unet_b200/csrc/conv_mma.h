@@ -39,6 +39,7 @@ struct alignas(64) ConvParams {
   const float* fuse_w;
   const float* fuse_b;
   int l2_prefetch;       // halo kernels: warm L2 with the boxes of the CTA's next work item
+  int a_collector;       // Cout >= 128 layers: A_hi stays in the tensor core's A collector for its second product
   // EPI_ACT
   int relu;
   int upsample;          // 1: write phase (pos>>1, pos&1) of a 2x upsampled map (ConvTranspose2d k=2,s=2)

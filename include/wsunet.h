@@ -56,7 +56,7 @@ int wsu_commit_weights(wsu_handle h);
  *          "fuse_e11" (default 0; 1: the first convolution is computed inside e12's producer warps and its feature map
  *                      never touches HBM - bit-identical but measured slower);
  *          "l2_prefetch" (default 0; 1: 3x3 kernels warm L2 with the boxes of their next work item - measured 1 % slower);
- *          "a_collector" (default 1: Cout >= 128 layers issue hi*hi, hi*lo, lo*hi and keep A_hi in the tensor core's
+ *          "a_collector" (default 1: the CTA-pair kernel issues hi*hi, hi*lo, lo*hi and keeps A_hi in the tensor core's
  *                         A collector for its second product; 0: every MMA re-reads A from shared memory);
  *          "cta_pair" (default 1: 3x3 layers with Cout >= 128 run as CTA pairs, tcgen05 cta_group::2; 0 never; 2 all);
  *          "upconv_resident" (default 1: transposed convs keep their weights in shared memory; 0: per-phase kernel);

@@ -692,15 +692,11 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
                     const uint64_t da_lo = make_sw128_desc(a_lo + k * 32, kHaloSBO);
                     const uint64_t dw_hi = make_sw128_desc(w_hi + k * 32);
                     const uint64_t dw_lo = make_sw128_desc(w_lo + k * 32);
-                    if (p.a_collector) {   // A_hi read once for its two products
-                      umma_bf16_a_fill(d, da_hi, dw_hi, idesc, (c | tap | k) != 0);
-                      umma_bf16_a_lastuse(d, da_hi, dw_lo, idesc, 1);
-                      umma_bf16(d, da_lo, dw_hi, idesc, 1);
-                    } else {
-                      umma_bf16(d, da_hi, dw_hi, idesc, (c | tap | k) != 0);
-                      umma_bf16(d, da_lo, dw_hi, idesc, 1);
-                      umma_bf16(d, da_hi, dw_lo, idesc, 1);
-                    }
+                    // (keeping A_hi in the A collector for hi*hi, hi*lo measured 4-8 % SLOWER in this single-CTA kernel,
+                    //  profiles/r01_layer_profile_a_collector.log; the CTA-pair kernel does use it)
+                    umma_bf16(d, da_hi, dw_hi, idesc, (c | tap | k) != 0);
+                    umma_bf16(d, da_lo, dw_hi, idesc, 1);
+                    umma_bf16(d, da_hi, dw_lo, idesc, 1);
                   }
                   if (tap == 8) umma_commit(&a_empty[a_slot[j]]);
                 }

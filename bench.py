@@ -158,6 +158,11 @@ def run_ours(args):
     import ws_unet_b200 as W
     from ws_unet_b200 import _native, parallel
 
+    # Libraries write banners to stdout (NCCL prints its version line there): keep the real stdout for the one JSON line
+    # and point fd 1 at stderr for everything else.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = parallel.init_from_env()
     if world != args.gpus:
         raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}')
@@ -295,8 +300,14 @@ def run_ours(args):
     conv_gflop = sum(layer_gflop[l['layer']] for l in layers if l['layer'] != 'e11') * (S / 512) ** 2
     achieved = conv_gflop * last_mb / (conv_ms * 1e-3) / 1e3 if conv_ms else 0.0
 
-    # ---- CPU baseline (reference's per-image path on this box's host cores), bounded sample
-    cpu_v, cpu_n, cores = cpu_baseline_run(seconds=args.cpu_seconds)
+    # ---- CPU baseline (reference's per-image path on this box's host cores), bounded sample; N = 1 only: under torchrun
+    # every rank is pinned to one OpenMP thread, which would not be the reference's configuration
+    cpu_base = None
+    if world == 1:
+        cpu_v, cpu_n, cores = cpu_baseline_run(seconds=args.cpu_seconds)
+        cpu_base = {'value': cpu_v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                    'sample': f'{cpu_n} images 512x512, batch 1, FP32, autograd on, torch ATen CPU ops exactly as '
+                              'src/unet/evaluate.py:31-52,125-132 calls them (oracle/torch_port.py)'}
 
     line = {
         'metric': METRIC if S == 512 else f'UNet-WS {S}x{S} images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -319,11 +330,9 @@ def run_ours(args):
                              'every MAC is issued as 3 bf16 MMAs (hi*hi, lo*hi, hi*lo), so issued = 3x algorithmic'},
         'layers': layers,
         'estimator': est,
-        'cpu_baseline': {'value': cpu_v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
-                         'sample': f'{cpu_n} images 512x512, batch 1, FP32, autograd on, torch ATen CPU ops exactly as '
-                                   'src/unet/evaluate.py:31-52,125-132 calls them (oracle/torch_port.py)'},
+        'cpu_baseline': cpu_base,
     }
-    print(json.dumps(line))
+    os.write(json_fd, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -316,7 +316,15 @@ def test_kernel_variants_agree(cuda_dev):
     lib.wsu_set_option(h, b'cta_pair', 1)
     lib.wsu_set_option(h, b'upconv_resident', 1)
     assert np.abs(outs[(1, 1, 1)] - outs[(0, 0, 0)]).max() * 255 < 1e-4
-    assert np.array_equal(outs[(1, 2, 1)], outs[(1, 0, 1)])   # CTA pairs issue the same MMAs: bit-identical
+    # CTA pairs keep A_hi in the A collector by default and issue hi*hi, hi*lo, lo*hi (single CTA: hi*hi, lo*hi, hi*lo):
+    # same products, different fp32 summation order. With the collector order off the two kernels are bit-identical.
+    assert np.abs(outs[(1, 2, 1)] - outs[(1, 0, 1)]).max() * 255 < 1e-4
+    lib.wsu_set_option(h, b'a_collector', 0)
+    lib.wsu_set_option(h, b'cta_pair', 2)
+    y_pair = m(xd).cpu().numpy()
+    lib.wsu_set_option(h, b'a_collector', 1)
+    lib.wsu_set_option(h, b'cta_pair', 1)
+    assert np.array_equal(y_pair, outs[(1, 0, 1)])
     # e11 fused into e12's producer warps vs materialised in HBM: same arithmetic, same bits (also on uint8 input)
     img8 = torch.randint(0, 256, (2, 1, 80, 112), dtype=torch.uint8, device=cuda_dev)
     for inp in (xd, img8):

@@ -153,6 +153,7 @@ struct wsu_context {
   // is off by default.
   bool fuse_e11 = false;
   int use_pair = 1;  // 3x3 layers as CTA pairs (tcgen05 cta_group::2): 0 never, 1 Cout>=128 layers (measured win), 2 all
+  int dbg = 0;            // env WSU_DBG: knock-out switches for timing experiments (results are wrong when set)
   int a_collector = 1;    // option "a_collector" (default on, +0.4 % measured): Cout >= 128 layers reuse A_hi from the A collector (hi*hi, hi*lo, lo*hi order)
   int l2_prefetch = 0;    // halo kernels prefetch the next item's boxes into L2 (option "l2_prefetch"); measured 1 % slower
   bool use_upres = true;  // transposed convs through upconv_res_kernel (option "upconv_resident")
@@ -412,6 +413,7 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
     const bool halo = h->use_halo && p.ntaps == 9;
     p.l2_prefetch = h->l2_prefetch;
     p.a_collector = h->a_collector;
+    p.dbg = h->dbg;
     if (nimg != pl.mb) {
       p.B = nimg;
       p.total_tiles = nimg * p.tiles_y * p.tiles_x * p.n_tiles * p.npos;
@@ -542,6 +544,7 @@ int wsu_create(wsu_handle* out, int device, int nsteps, int in_channels, int out
   if (const char* e = std::getenv("WSU_FUSE_E11")) h->fuse_e11 = std::atoi(e) != 0;
   if (const char* e = std::getenv("WSU_HALO")) h->use_halo = std::atoi(e) != 0;
   if (const char* e = std::getenv("WSU_A_COLLECTOR")) h->a_collector = std::atoi(e) != 0;
+  if (const char* e = std::getenv("WSU_DBG")) h->dbg = std::atoi(e);
   *out = h;
   return WSU_OK;
 }

@@ -77,6 +77,26 @@ __device__ __forceinline__ void store_pixel32(const Act& o, int b, int oy, int o
   }
 }
 
+// store 8 channels (one 16-byte piece per plane) of one pixel to every halo target of (oy, ox)
+__device__ __forceinline__ void store_pixel8(const Act& o, int b, int oy, int ox, int c0, const uint32_t (&h)[4],
+                                             const uint32_t (&l)[4]) {
+  const uint4 vh = make_uint4(h[0], h[1], h[2], h[3]), vl = make_uint4(l[0], l[1], l[2], l[3]);
+  const size_t off = ((size_t(b) * (o.H + 2) + (oy + 1)) * (o.W + 2) + (ox + 1)) * o.C + c0;
+  *reinterpret_cast<uint4*>(o.base + off) = vh;
+  *reinterpret_cast<uint4*>(o.base + o.plane + off) = vl;
+  if (oy == 1 || ox == 1 || oy == o.H - 2 || ox == o.W - 2) {   // reflect-halo duplicates (border pixels only)
+    int ys[3], xs[3];
+    const int ny = halo_targets(oy, o.H, ys), nx = halo_targets(ox, o.W, xs);
+    for (int iy = 0; iy < ny; ++iy)
+      for (int ix = 0; ix < nx; ++ix) {
+        if (iy == 0 && ix == 0) continue;   // (oy+1, ox+1) itself was written above
+        const size_t d = ((size_t(b) * (o.H + 2) + ys[iy]) * (o.W + 2) + xs[ix]) * o.C + c0;
+        *reinterpret_cast<uint4*>(o.base + d) = vh;
+        *reinterpret_cast<uint4*>(o.base + o.plane + d) = vl;
+      }
+  }
+}
+
 // Epilogue of one 128-pixel box: thread owns pixel (y, x) = TMEM lane; tbase addresses its accumulator columns.
 // pool_xor: lane distance of the vertical 2x2-pool partner (= box width in pixels).
 // Geometry of the 128-pixel box a warp is finishing: row r of the box <-> pixel (y0 + (r >> tw_shift), x0 + (r & mask)).
@@ -91,12 +111,38 @@ struct BoxGeo {
   }
 };
 
+// Where this lane's four (pixel, 16-byte piece) stores of a chunk go: computed once per box, reused by every
+// 32-channel chunk and both planes. Lane l re-reads pixel q = (l >> 2) + 8 i, piece l & 3 from the staging buffer.
+// `border`: at least one of the warp's pixels also owns reflect-halo slots -> the generic path writes the duplicates.
+struct StoreMap {
+  size_t off[4];   // element offset of (pixel, channel 0) in a plane; only meaningful where (valid >> i) & 1
+  uint32_t valid;
+  bool border;
+};
+__device__ __forceinline__ StoreMap make_store_map(const Act& o, const BoxGeo& g, int lane, int row0) {
+  StoreMap m;
+  m.valid = 0;
+  bool edge = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int q = (lane >> 2) + 8 * i;
+    int oy, ox;
+    const bool ok = g.pixel(row0 + q, oy, ox);
+    m.off[i] = ((size_t(g.b) * (o.H + 2) + (oy + 1)) * (o.W + 2) + (ox + 1)) * o.C;
+    m.valid |= uint32_t(ok) << i;
+    edge |= ok && (oy == 1 || ox == 1 || oy == o.H - 2 || ox == o.W - 2);
+  }
+  m.border = __any_sync(0xffffffffu, edge);
+  return m;
+}
+
 // Warp-cooperative store of one 32-channel chunk of the warp's 32 pixels. Registers hold "my pixel, 32 channels";
 // a 64-byte row per pixel is staged in shared memory and re-read so that 4 consecutive lanes write the 4 consecutive
 // 16-byte pieces of one pixel: a store instruction then touches 8 half-lines instead of 32 different lines
 // (uncoalesced 16-byte stores made the LSU, not the tensor pipe, the limiter of the store-heavy layers).
 __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scratch, int lane, int row0, int c0,
-                                                      const uint32_t (&h)[16], const uint32_t (&l)[16], const BoxGeo& g) {
+                                                      const uint32_t (&h)[16], const uint32_t (&l)[16], const BoxGeo& g,
+                                                      const StoreMap& map) {
   const int piece = lane & 3;
 #pragma unroll
   for (int plane = 0; plane < 2; ++plane) {
@@ -107,20 +153,30 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
       mine[q] = plane ? make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3])
                       : make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
     __syncwarp();
-    __nv_bfloat16* base = o.base + (plane ? o.plane : 0);
+    __nv_bfloat16* base = o.base + (plane ? o.plane : 0) + c0 + piece * 8;
+    if (!map.border) {
+      // interior box: one store per (pixel, piece), addresses from the per-box map
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int q = (lane >> 2) + 8 * i;
-      const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * kScratchPitch + piece * 16);
-      int oy, ox;
-      if (g.pixel(row0 + q, oy, ox)) {
-        int ys[3], xs[3];
-        const int ny = halo_targets(oy, o.H, ys), nx = halo_targets(ox, o.W, xs);
-        for (int iy = 0; iy < ny; ++iy)
-          for (int ix = 0; ix < nx; ++ix) {
-            const size_t off = ((size_t(g.b) * (o.H + 2) + ys[iy]) * (o.W + 2) + xs[ix]) * o.C + c0 + piece * 8;
-            *reinterpret_cast<uint4*>(base + off) = v;
-          }
+      for (int i = 0; i < 4; ++i) {
+        const int q = (lane >> 2) + 8 * i;
+        const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * kScratchPitch + piece * 16);
+        if ((map.valid >> i) & 1) *reinterpret_cast<uint4*>(base + map.off[i]) = v;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = (lane >> 2) + 8 * i;
+        const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * kScratchPitch + piece * 16);
+        int oy, ox;
+        if (g.pixel(row0 + q, oy, ox)) {
+          int ys[3], xs[3];
+          const int ny = halo_targets(oy, o.H, ys), nx = halo_targets(ox, o.W, xs);
+          for (int iy = 0; iy < ny; ++iy)
+            for (int ix = 0; ix < nx; ++ix) {
+              const size_t off = ((size_t(g.b) * (o.H + 2) + ys[iy]) * (o.W + 2) + xs[ix]) * o.C;
+              *reinterpret_cast<uint4*>(base + off) = v;
+            }
+        }
       }
     }
   }
@@ -150,6 +206,7 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
                                        bool valid, int nt, int pos, int tx, int ty, int pool_xor, WsAcc& acc,
                                        const BoxGeo& geo, uint8_t* scratch, int lane, int row0) {
   if constexpr (EPI == EPI_ACT) {
+    const StoreMap smap = make_store_map(p.out, geo, lane, row0);
 #pragma unroll 1
     for (int cc = 0; cc < N_TILE / 32; ++cc) {
       const int n0 = nt * N_TILE + cc * 32;
@@ -163,18 +220,28 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
       uint32_t h[16], l[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
-      store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo);
-      if (p.do_pool) {
-        // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16)
+      if (!(p.dbg & 2)) store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap);
+      if (p.do_pool && !(p.dbg & 1)) {
+        // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16). Each exchange moves
+        // only the half the partner will keep, so the four lanes of a quad end up with 8 channels each of the pooled
+        // pixel (24 shuffles per chunk instead of 64) and every lane stores one 16-byte piece per plane.
+        const bool ox1 = tx & 1, oy1 = ty & 1;
+        float m16[16], m8[8];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], 1));
-          f[i] = fmaxf(f[i], __shfl_xor_sync(0xffffffffu, f[i], pool_xor));
+        for (int i = 0; i < 16; ++i) {
+          const float keep = ox1 ? f[16 + i] : f[i], send = ox1 ? f[i] : f[16 + i];
+          m16[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
         }
-        if (valid && !(tx & 1) && !(ty & 1)) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
-          store_pixel32(p.pool, b, y >> 1, x >> 1, n0, h, l);
+        for (int i = 0; i < 8; ++i) {
+          const float keep = oy1 ? m16[8 + i] : m16[i], send = oy1 ? m16[i] : m16[8 + i];
+          m8[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, pool_xor));
+        }
+        if (valid) {
+          uint32_t h4[4], l4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_pack2(m8[2 * i], m8[2 * i + 1], h4[i], l4[i]);
+          store_pixel8(p.pool, b, y >> 1, x >> 1, n0 + 16 * int(ox1) + 8 * int(oy1), h4, l4);
         }
       }
     }
@@ -1172,7 +1239,9 @@ __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_
         for (int i = 0; i < 16; ++i)
           split_pack2(__uint_as_float(v[2 * i]) + sBias[cl + 2 * i], __uint_as_float(v[2 * i + 1]) + sBias[cl + 2 * i + 1], h[i], l[i]);
         const BoxGeo geo{b, ty * 8, tx * 16, 4, p.H, p.W, 1, pos};
-        store_chunk_coalesced(p.out, sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32, nt * p.co_t + cl, h, l, geo);
+        const StoreMap smap = make_store_map(p.out, geo, lane, quad * 32);   // per chunk: the output phase changes with it
+        store_chunk_coalesced(p.out, sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32, nt * p.co_t + cl, h, l, geo,
+                              smap);
       }
       tc_fence_before();
       __syncwarp();

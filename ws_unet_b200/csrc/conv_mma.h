@@ -39,6 +39,7 @@ struct alignas(64) ConvParams {
   const float* fuse_w;
   const float* fuse_b;
   int l2_prefetch;       // halo kernels: warm L2 with the boxes of the CTA's next work item
+  int dbg;               // timing experiments only (env WSU_DBG): bit 0 skips the pooled output, bit 1 the main output stores
   int a_collector;       // Cout >= 128 layers: A_hi stays in the tensor core's A collector for its second product
   // EPI_ACT
   int relu;

@@ -567,12 +567,12 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
     // ===================================================== fused e11 producer (3 warps): compute the haloed box in place
     const int t = threadIdx.x - 11 * 32;
     const int q = t & 7;                       // this thread's 8 output channels = one 16-byte piece of a pixel row
-    float wr[8][9], bs[8];
+    uint64_t wr[4][9], bs[4];   // fp32 pairs: one FFMA2 advances two output channels
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      bs[i] = p.fuse_b[q * 8 + i];
+    for (int i = 0; i < 4; ++i) {
+      bs[i] = pack_f32x2(p.fuse_b[q * 8 + 2 * i], p.fuse_b[q * 8 + 2 * i + 1]);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) wr[i][k] = p.fuse_w[(q * 8 + i) * 9 + k];
+      for (int k = 0; k < 9; ++k) wr[i][k] = pack_f32x2(p.fuse_w[(q * 8 + 2 * i) * 9 + k], p.fuse_w[(q * 8 + 2 * i + 1) * 9 + k]);
     }
     const int H = p.H, W = p.W;
     int as = 0;
@@ -600,20 +600,24 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
           const int yy = reflect_clamp(bc.y0 - 1 + py, H), xx = reflect_clamp(bc.x0 - 1 + px, W);
           const int ry = min(max(yy - (bc.y0 - 2), 1), 18), rx = min(max(xx - (bc.x0 - 2), 1), 10);
           const float* win = sPatch + (ry - 1) * 12 + (rx - 1);
-          float acc[8];
+          uint64_t acc[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = bs[i];
+          for (int i = 0; i < 4; ++i) acc[i] = bs[i];
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
               const float v = win[dy * 12 + dx];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, wr[i][dy * 3 + dx], acc[i]);
+              for (int i = 0; i < 4; ++i) acc[i] = fma2_bcast(v, wr[i][dy * 3 + dx], acc[i]);
             }
           uint32_t h[4], l[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) split_pack2(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f), h[i], l[i]);
+          for (int i = 0; i < 4; ++i) {
+            float a0, a1;
+            unpack_f32x2(acc[i], a0, a1);
+            split_pack2(fmaxf(a0, 0.f), fmaxf(a1, 0.f), h[i], l[i]);
+          }
           // SWIZZLE_128B on absolute address bits: the lo plane starts 180 rows in, i.e. at row phase (pix + 4) & 7
           *reinterpret_cast<uint4*>(slot + pix * 128 + ((q ^ (pix & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
           *reinterpret_cast<uint4*>(slot + kHaloRows * 128 + pix * 128 + ((q ^ ((pix + 4) & 7)) << 4)) =

@@ -52,12 +52,14 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict_
     rows[ci][r][col] = v;
   }
   const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  float wr[8][CIN * 9], bs[8];
+  // weights / accumulators as fp32 pairs: one FFMA2 advances two output channels
+  uint64_t wr[4][CIN * 9], bs[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    bs[i] = bias[cg * 8 + i];
+  for (int i = 0; i < 4; ++i) {
+    bs[i] = pack_f32x2(bias[cg * 8 + 2 * i], bias[cg * 8 + 2 * i + 1]);
 #pragma unroll
-    for (int t = 0; t < CIN * 9; ++t) wr[i][t] = w[(cg * 8 + i) * CIN * 9 + t];
+    for (int t = 0; t < CIN * 9; ++t)
+      wr[i][t] = pack_f32x2(w[(cg * 8 + 2 * i) * CIN * 9 + t], w[(cg * 8 + 2 * i + 1) * CIN * 9 + t]);
   }
   __syncthreads();
 #pragma unroll 1
@@ -68,9 +70,9 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict_
     const int x = x0 + lx;
     if (y >= H) break;
     if (x >= W) continue;
-    float acc[8];
+    uint64_t acc[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = bs[i];
+    for (int i = 0; i < 4; ++i) acc[i] = bs[i];
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci)
 #pragma unroll
@@ -79,19 +81,30 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict_
         for (int dx = 0; dx < 3; ++dx) {
           const float v = rows[ci][ry + dy][lx + dx];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, wr[i][ci * 9 + dy * 3 + dx], acc[i]);
+          for (int i = 0; i < 4; ++i) acc[i] = fma2_bcast(v, wr[i][ci * 9 + dy * 3 + dx], acc[i]);
         }
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) split_pack2(fmaxf(acc[2 * i], 0.f), fmaxf(acc[2 * i + 1], 0.f), h[i], l[i]);
-    int ys[3], xs[3];
-    const int ny = halo_targets(y, H, ys), nx = halo_targets(x, W, xs);
-    for (int iy = 0; iy < ny; ++iy)
-      for (int ix = 0; ix < nx; ++ix) {
-        const size_t off = ((size_t(b) * (H + 2) + ys[iy]) * (W + 2) + xs[ix]) * out.C + cg * 8;
-        *reinterpret_cast<uint4*>(out.base + off) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(out.base + out.plane + off) = make_uint4(l[0], l[1], l[2], l[3]);
-      }
+    for (int i = 0; i < 4; ++i) {
+      float a0, a1;
+      unpack_f32x2(acc[i], a0, a1);
+      split_pack2(fmaxf(a0, 0.f), fmaxf(a1, 0.f), h[i], l[i]);
+    }
+    const uint4 vh = make_uint4(h[0], h[1], h[2], h[3]), vl = make_uint4(l[0], l[1], l[2], l[3]);
+    const size_t off0 = ((size_t(b) * (H + 2) + (y + 1)) * (W + 2) + (x + 1)) * out.C + cg * 8;
+    *reinterpret_cast<uint4*>(out.base + off0) = vh;
+    *reinterpret_cast<uint4*>(out.base + out.plane + off0) = vl;
+    if (y == 1 || x == 1 || y == H - 2 || x == W - 2) {   // reflect-halo duplicates (border pixels only)
+      int ys[3], xs[3];
+      const int ny = halo_targets(y, H, ys), nx = halo_targets(x, W, xs);
+      for (int iy = 0; iy < ny; ++iy)
+        for (int ix = 0; ix < nx; ++ix) {
+          if (iy == 0 && ix == 0) continue;
+          const size_t off = ((size_t(b) * (H + 2) + ys[iy]) * (W + 2) + xs[ix]) * out.C + cg * 8;
+          *reinterpret_cast<uint4*>(out.base + off) = vh;
+          *reinterpret_cast<uint4*>(out.base + out.plane + off) = vl;
+        }
+    }
   }
 }
 

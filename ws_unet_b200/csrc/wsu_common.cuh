@@ -41,6 +41,23 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi2, uin
   lo2 = cvt_bf16x2(a - ah, b - bh);  // a - ah is exact in fp32 (Sterbenz-like: ah is a rounded to 8 bits)
 }
 
+// Packed fp32 pair arithmetic (Blackwell FFMA2): acc.{lo,hi} = fma.rn(v, w.{lo,hi}, acc.{lo,hi}) - two independent IEEE
+// fused multiply-adds (bit-identical to two fmaf calls) in one instruction of the FMA pipe.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2_bcast(float v, uint64_t w, uint64_t acc) {
+  uint64_t vv, d;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(vv) : "f"(v));   // ptxas folds this into the scalar-broadcast operand form
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(vv), "l"(w), "l"(acc));
+  return d;
+}
+
 // Reflect-halo targets of a logical coordinate v in [0,n): storage index v+1, plus the mirrored border
 // rows/cols it also owns (index 0 mirrors logical 1, index n+1 mirrors logical n-2).
 __device__ __forceinline__ int halo_targets(int v, int n, int (&t)[3]) {

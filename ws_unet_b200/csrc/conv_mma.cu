@@ -869,7 +869,7 @@ struct H2Cfg {
   static constexpr int SMEM = SA * kHaloABytes + SW * W_SLOT + kScratchBytes + 1024 + BIAS_BYTES + 256;
 };
 
-template <int N_TILE, int EPI>
+template <int N_TILE, int EPI, bool COLL = true>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __grid_constant__ ConvParams p) {
   using C = H2Cfg<N_TILE>;
   constexpr int M_SUB = C::M_SUB;
@@ -1023,7 +1023,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
                       umma_bf16_2sm(d, da_hi, dw_x, make_idesc_bf16_m(256, 128), (c | tap | k) != 0);  // Ahi * [Whi; Wlo]
                       umma_bf16_2sm(d, da_lo, dw_y, make_idesc_bf16_m(256, 64), 1);                    // Alo * Whi
                     } else {
-                      if (p.a_collector) {   // A_hi read once for its two products
+                      if constexpr (COLL) {   // A_hi read once for its two products (compile-time: a runtime branch in this
+                                              // single-thread issue loop costs ~10 % of the layer)
                         umma_bf16_2sm_a_fill(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
                         umma_bf16_2sm_a_lastuse(d, da_hi, dw_y, idesc, 1);
                         umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
@@ -1118,7 +1119,8 @@ cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<N_TILE, EPI>, p);
+  if (N_TILE == 128 && !p.a_collector) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<N_TILE, EPI, false>, p);
+  return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<N_TILE, EPI, true>, p);
 }
 
 // ================================================================================================ resident-weight upconv
@@ -1283,6 +1285,8 @@ cudaError_t conv_mma_init() {
   e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
   if (e != cudaSuccess) return e;

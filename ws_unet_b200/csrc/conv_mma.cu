@@ -714,16 +714,15 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
                       if (++as == C::SA) { as = 0; aph ^= 1; }
                     }
                     tc_fence_after();
-                    const uint32_t w_hi = smem_u32(sW + wslot[tt] * C::W_BYTES);
+                    const uint64_t wd = make_sw128_desc(smem_u32(sW + wslot[tt] * C::W_BYTES));
+                    const uint64_t ad = make_sw128_desc(smem_u32(sA + a_slot[j] * kHaloABytes), kHaloSBO);
                     const uint32_t tap_off = uint32_t(g * (kHaloTW + 2) + tt) * 128;
-                    const uint32_t a_hi = smem_u32(sA + a_slot[j] * kHaloABytes) + tap_off;
-                    const uint32_t a_lo = a_hi + kHaloRows * 128;
                     const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                      const uint64_t da_hi = make_sw128_desc(a_hi + k * 32, kHaloSBO);
-                      const uint64_t da_lo = make_sw128_desc(a_lo + k * 32, kHaloSBO);
-                      const uint64_t dw_hi = make_sw128_desc(w_hi + k * 32);
+                      const uint64_t da_hi = desc_at(desc_lo(ad), desc_hi(ad), tap_off + k * 32);
+                      const uint64_t da_lo = desc_at(desc_lo(ad), desc_hi(ad), tap_off + kHaloRows * 128 + k * 32);
+                      const uint64_t dw_hi = desc_at(desc_lo(wd), desc_hi(wd), k * 32);
                       // B tile of 128 rows = [Whi; Wlo]: columns [0,64) += Ahi*Whi, [64,128) += Ahi*Wlo
                       umma_bf16(d, da_hi, dw_hi, make_idesc_bf16(128), (c | tap | k) != 0);
                       umma_bf16(d, da_lo, dw_hi, make_idesc_bf16(64), 1);   // columns [0,64) += Alo*Whi
@@ -754,15 +753,15 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
                     if (++as == C::SA) { as = 0; aph ^= 1; }
                   }
                   tc_fence_after();
-                  const uint32_t a_hi = smem_u32(sA + a_slot[j] * kHaloABytes) + tap_off;
-                  const uint32_t a_lo = a_hi + kHaloRows * 128;
+                  const uint64_t ad = make_sw128_desc(smem_u32(sA + a_slot[j] * kHaloABytes), kHaloSBO);
+                  const uint64_t whd = make_sw128_desc(w_hi), wld = make_sw128_desc(w_lo);
                   const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const uint64_t da_hi = make_sw128_desc(a_hi + k * 32, kHaloSBO);
-                    const uint64_t da_lo = make_sw128_desc(a_lo + k * 32, kHaloSBO);
-                    const uint64_t dw_hi = make_sw128_desc(w_hi + k * 32);
-                    const uint64_t dw_lo = make_sw128_desc(w_lo + k * 32);
+                    const uint64_t da_hi = desc_at(desc_lo(ad), desc_hi(ad), tap_off + k * 32);
+                    const uint64_t da_lo = desc_at(desc_lo(ad), desc_hi(ad), tap_off + kHaloRows * 128 + k * 32);
+                    const uint64_t dw_hi = desc_at(desc_lo(whd), desc_hi(whd), k * 32);
+                    const uint64_t dw_lo = desc_at(desc_lo(wld), desc_hi(wld), k * 32);
                     // (keeping A_hi in the A collector for hi*hi, hi*lo measured 4-8 % SLOWER in this single-CTA kernel,
                     //  profiles/r01_layer_profile_a_collector.log; the CTA-pair kernel does use it)
                     umma_bf16(d, da_hi, dw_hi, idesc, (c | tap | k) != 0);
@@ -1010,15 +1009,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
                     if (++as == C::SA) { as = 0; aph ^= 1; }
                   }
                   tc_fence_after();
-                  const uint32_t a_hi = smem_u32(sA + a_slot[j] * kHaloABytes) + tap_off;
-                  const uint32_t a_lo = a_hi + kHaloRows * 128;
+                  const uint64_t ad = make_sw128_desc(smem_u32(sA + a_slot[j] * kHaloABytes), kHaloSBO);
+                  const uint64_t wxd = make_sw128_desc(w_x), wyd = make_sw128_desc(w_y);
                   const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-                    const uint64_t da_hi = make_sw128_desc(a_hi + k * 32, kHaloSBO);
-                    const uint64_t da_lo = make_sw128_desc(a_lo + k * 32, kHaloSBO);
-                    const uint64_t dw_x = make_sw128_desc(w_x + k * 32);
-                    const uint64_t dw_y = make_sw128_desc(w_y + k * 32);
+                    const uint64_t da_hi = desc_at(desc_lo(ad), desc_hi(ad), tap_off + k * 32);
+                    const uint64_t da_lo = desc_at(desc_lo(ad), desc_hi(ad), tap_off + kHaloRows * 128 + k * 32);
+                    const uint64_t dw_x = desc_at(desc_lo(wxd), desc_hi(wxd), k * 32);
+                    const uint64_t dw_y = desc_at(desc_lo(wyd), desc_hi(wyd), k * 32);
                     if constexpr (C::STACKED) {
                       umma_bf16_2sm(d, da_hi, dw_x, make_idesc_bf16_m(256, 128), (c | tap | k) != 0);  // Ahi * [Whi; Wlo]
                       umma_bf16_2sm(d, da_lo, dw_y, make_idesc_bf16_m(256, 64), 1);                    // Alo * Whi

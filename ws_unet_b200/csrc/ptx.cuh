@@ -155,6 +155,14 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
   d |= uint64_t(2) << 61;                        // SWIZZLE_128B
   return d;
 }
+// The start address lives in the low 14 bits of the descriptor's low word (bytes >> 4) and shared memory ends below
+// 2^18 bytes, so stepping a descriptor through a tile is ONE 32-bit add on the low word: the single issuing thread then
+// spends one uniform-datapath instruction per descriptor instead of re-deriving the whole bit field (mask, shift, or).
+__device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return uint32_t(d); }
+__device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return uint32_t(d >> 32); }
+__device__ __forceinline__ uint64_t desc_at(uint32_t lo, uint32_t hi, uint32_t byte_off) {
+  return (uint64_t(hi) << 32) | uint64_t(lo + (byte_off >> 4));
+}
 // Instruction descriptor: bf16 A/B (K-major), f32 accumulate, M=128, N=n.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(128 >> 4) << 24);

@@ -232,6 +232,10 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     lib.wsu_launch_count(1)
+    h = model.native_handle(dev)
+    # per-layer CUDA events (on the launching stream) stay on during the timed steps: the roofline below is taken from
+    # the last micro-batch INSIDE the timed region, at the clocks the step sustains (24 event records per micro-batch)
+    lib.wsu_set_option(h, b'profile', 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -239,6 +243,12 @@ def run_ours(args):
     e1.record()
     barrier()
     launches = lib.wsu_launch_count(0)
+    prof_buf = (ctypes.c_float * 64)()
+    n_layers = lib.wsu_profile_read(h, prof_buf, 64) if rank == 0 else 0
+    prof_info = ctypes.c_int64()
+    lib.wsu_get_info(h, b'last_images', ctypes.byref(prof_info))
+    last_mb = int(prof_info.value)
+    lib.wsu_set_option(h, b'profile', 0)
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -248,7 +258,6 @@ def run_ours(args):
     value = n_total * args.steps / (ms_max / 1e3)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory -> H2D -> chain -> D2H)
-    h = model.native_handle(dev)
     host_img = imgs.cpu().pin_memory()
     host_out = torch.empty(2, per_gpu, dtype=torch.float32).pin_memory()
 
@@ -276,19 +285,11 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- per-layer device times (one extra profiled step, rank 0) -> roofline of the tensor-core chain
-    lib.wsu_set_option(h, b'profile', 1)
-    lib.wsu_get_info(h, b'micro_batch', ctypes.byref(ctypes.c_int64()))
-    W.ws_estimate(imgs[:args.profile_images], model, weighted=0, clip=True, crop=1)  # one full micro-batch
-    torch.cuda.synchronize()
-    buf = (ctypes.c_float * 64)()
-    n_layers = lib.wsu_profile_read(h, buf, 64)
-    lib.wsu_set_option(h, b'profile', 0)
+    # ---- per-layer device times of the last micro-batch of the timed region -> roofline of the tensor-core chain
+    buf = prof_buf
     info = ctypes.c_int64()
     lib.wsu_get_info(h, b'micro_batch', ctypes.byref(info))
     mb = int(info.value)
-    lib.wsu_get_info(h, b'last_images', ctypes.byref(info))
-    last_mb = int(info.value)
     layer_gflop = {'e11': 0.302, 'e12': 19.327, 'e21': 9.664, 'e22': 19.327, 'e31': 9.664, 'e32': 19.327, 'upconv3': 4.295,
                    'd31': 38.655, 'd32': 19.327, 'upconv4': 4.295, 'd41': 38.655, 'd42': 19.327 + 0.034}
     layers = []
@@ -326,7 +327,7 @@ def run_ours(args):
                      'frac': achieved / pk['tf_sustained'], 'traffic': 0.922e9 * last_mb * (S / 512) ** 2, 'traffic_note': 'dram__bytes_read+write summed over the 11 launches of a 32-image pass from the ncu --set full capture in profiles/r01_ncu_halo_kernels.md (0.922 GB per 512x512 image), scaled to this pass', 'peak_source': pk['source'] + ' sustained bf16',
                      'kernel': 'conv_halo_kernel / conv_halo2_kernel / upconv_res_kernel (11 tensor-core launches per micro-batch)', 'issued_tflops': 3 * achieved,
                      'issued_frac': 3 * achieved / pk['tf_sustained'],
-                     'note': 'achieved = algorithmic 2*MACs of the 11 tensor-core layers / their summed CUDA-event time; '
+                     'note': 'achieved = algorithmic 2*MACs of the 11 tensor-core layers / their summed CUDA-event time in the last micro-batch of the timed region; '
                              'every MAC is issued as 3 bf16 MMAs (hi*hi, lo*hi, hi*lo), so issued = 3x algorithmic'},
         'layers': layers,
         'estimator': est,

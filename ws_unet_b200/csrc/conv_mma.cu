@@ -24,8 +24,12 @@ namespace {
 constexpr int kThreads = 320;          // warps: 0 TMA, 1 MMA, 2..9 epilogue (two groups of four lane quadrants)
 constexpr int kABytes = 2 * 128 * 128;  // hi + lo tile of 128 pixels x 64 channels
 constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
-constexpr int kScratchPitch = 80;                       // 64 B of payload + 16 B pad: conflict-free 16-byte writes
-constexpr int kScratchPerWarp = 32 * kScratchPitch;     // 2560 B of epilogue staging per warp
+constexpr int kScratchPitch = 64;                       // dense 64-byte rows; the 16-byte piece index is XOR-swizzled with
+                                                        // (row >> 1) & 3, which makes BOTH the lane-major writes and the
+                                                        // 4-lanes-per-pixel reads bank-conflict free (an 80-byte padded
+                                                        // pitch left the reads 2-way conflicted: the LSU data pipe, not
+                                                        // DRAM, was what bounded the up-convolutions)
+constexpr int kScratchPerWarp = 32 * kScratchPitch;     // 2048 B of epilogue staging per warp
 constexpr int kScratchBytes = 8 * kScratchPerWarp;      // eight epilogue warps
 
 template <int N_TILE>
@@ -148,10 +152,11 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
   for (int plane = 0; plane < 2; ++plane) {
     __syncwarp();
     uint4* mine = reinterpret_cast<uint4*>(scratch + lane * kScratchPitch);
+    const int wsw = (lane >> 1) & 3;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      mine[q] = plane ? make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3])
-                      : make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+      mine[q ^ wsw] = plane ? make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3])
+                            : make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
     __syncwarp();
     __nv_bfloat16* base = o.base + (plane ? o.plane : 0) + c0 + piece * 8;
     if (!map.border) {
@@ -159,14 +164,14 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int q = (lane >> 2) + 8 * i;
-        const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * kScratchPitch + piece * 16);
+        const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * kScratchPitch + ((piece ^ ((q >> 1) & 3)) << 4));
         if ((map.valid >> i) & 1) *reinterpret_cast<uint4*>(base + map.off[i]) = v;
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int q = (lane >> 2) + 8 * i;
-        const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * kScratchPitch + piece * 16);
+        const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * kScratchPitch + ((piece ^ ((q >> 1) & 3)) << 4));
         int oy, ox;
         if (g.pixel(row0 + q, oy, ox)) {
           int ys[3], xs[3];
@@ -213,9 +218,13 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
       float f[32];
       load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        f[i] += sBias[n0 + i];
-        if (p.relu) f[i] = fmaxf(f[i], 0.f);
+      for (int i = 0; i < 8; ++i) {   // 128-bit broadcast loads: 8 instead of 32 shared-memory wavefronts per chunk
+        const float4 bq = *reinterpret_cast<const float4*>(sBias + n0 + 4 * i);
+        f[4 * i] += bq.x; f[4 * i + 1] += bq.y; f[4 * i + 2] += bq.z; f[4 * i + 3] += bq.w;
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
       }
       uint32_t h[16], l[16];
 #pragma unroll
@@ -253,9 +262,12 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
       float f[32];
       load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float a = fmaxf(f[i] + sBias[cc * 32 + i], 0.f);
-        z = fmaf(a, p.wout[cc * 32 + i], z);
+      for (int i = 0; i < 8; ++i) {
+        const float4 bq = *reinterpret_cast<const float4*>(sBias + cc * 32 + 4 * i);
+        z = fmaf(fmaxf(f[4 * i] + bq.x, 0.f), p.wout[cc * 32 + 4 * i], z);
+        z = fmaf(fmaxf(f[4 * i + 1] + bq.y, 0.f), p.wout[cc * 32 + 4 * i + 1], z);
+        z = fmaf(fmaxf(f[4 * i + 2] + bq.z, 0.f), p.wout[cc * 32 + 4 * i + 2], z);
+        z = fmaf(fmaxf(f[4 * i + 3] + bq.w, 0.f), p.wout[cc * 32 + 4 * i + 3], z);
       }
     }
     if (valid) {
@@ -1241,8 +1253,11 @@ __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_
         const int pos = col0 / p.co_t, cl = col0 % p.co_t;
         uint32_t h[16], l[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          split_pack2(__uint_as_float(v[2 * i]) + sBias[cl + 2 * i], __uint_as_float(v[2 * i + 1]) + sBias[cl + 2 * i + 1], h[i], l[i]);
+        for (int i = 0; i < 8; ++i) {
+          const float4 bq = *reinterpret_cast<const float4*>(sBias + cl + 4 * i);
+          split_pack2(__uint_as_float(v[4 * i]) + bq.x, __uint_as_float(v[4 * i + 1]) + bq.y, h[2 * i], l[2 * i]);
+          split_pack2(__uint_as_float(v[4 * i + 2]) + bq.z, __uint_as_float(v[4 * i + 3]) + bq.w, h[2 * i + 1], l[2 * i + 1]);
+        }
         const BoxGeo geo{b, ty * 8, tx * 16, 4, p.H, p.W, 1, pos};
         const StoreMap smap = make_store_map(p.out, geo, lane, quad * 32);   // per chunk: the output phase changes with it
         store_chunk_coalesced(p.out, sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32, nt * p.co_t + cl, h, l, geo,

@@ -349,7 +349,6 @@ def main():
     ap.add_argument('--micro-batch', type=int, default=0)
     ap.add_argument('--est-images', type=int, default=10000, help='images of the KB-filter estimator measurement (configs[1]); 0 skips it (launch lists of the UNet step)')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
-    ap.add_argument('--profile-images', type=int, default=32, help='images of the per-layer profiled pass')
     ap.add_argument('--size', type=int, default=512, help='image side; 1024 = BASELINE configs[4] (not the headline metric)')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':

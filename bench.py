@@ -325,6 +325,8 @@ def run_ours(args):
         'gpu_launches': int(launches),
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
                      'frac': achieved / pk['tf_sustained'], 'traffic': 0.922e9 * last_mb * (S / 512) ** 2, 'traffic_note': 'dram__bytes_read+write summed over the 11 launches of a 32-image pass from the ncu --set full capture in profiles/r01_ncu_halo_kernels.md (0.922 GB per 512x512 image), scaled to this pass', 'peak_source': pk['source'] + ' sustained bf16',
+                     'tensor_pipe_active_pct_ncu': {'cout_ge_128_cta_pair': [73.8, 89.6], 'cout_64': [62.4, 71.3], 'upconv': [26.7, 39.9],
+                                                    'source': 'profiles/r01_ncu_chain_final.md (ncu --set full, sm__pipe_tensor_cycles_active, not measured in this run)'},
                      'kernel': 'conv_halo_kernel / conv_halo2_kernel / upconv_res_kernel (11 tensor-core launches per micro-batch)', 'issued_tflops': 3 * achieved,
                      'issued_frac': 3 * achieved / pk['tf_sustained'],
                      'note': 'achieved = algorithmic 2*MACs of the 11 tensor-core layers / their summed CUDA-event time in the last micro-batch of the timed region; '

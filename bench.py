@@ -212,7 +212,18 @@ def run_ours(args):
                                        'frac': gbs / pk['hbm_gbs'], 'bound': 'hbm', 'images': n_est,
                                        'kernel': 'filter_ws_adjoint_kernel + finalize_kernel' if weighted == 0
                                        else 'filter_ws_window_kernel + finalize_kernel'}
-        del est_imgs
+        # the same estimator end to end from pinned host memory (H2D copy inside the timed region): PCIe-bound
+        n_h = min(n_est, 2048)
+        host_est = est_imgs[:n_h].cpu().pin_memory()
+        for _ in range(2):
+            W.ws_estimate_host(host_est, 'KB', weighted=0)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            W.ws_estimate_host(host_est, 'KB', weighted=0)
+        dt = (time.perf_counter() - t0) / 3
+        est['kb_w0_e2e'] = {'images_per_s': n_h / dt, 'h2d_gbs': S * S * n_h / dt / 1e9, 'images': n_h,
+                            'note': 'wsu_filter_ws_estimate_host: pinned host uint8 -> H2D -> kernel -> D2H, bound by the host link'}
+        del est_imgs, host_est
         est['clocks'] = est_sampler.stop()
         torch.cuda.empty_cache()
 

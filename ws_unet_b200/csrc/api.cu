@@ -42,6 +42,26 @@ int fail(int code, const std::string& msg) {
       return fail(WSU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
   } while (0)
 
+// Every entry point runs on the device it was asked for and leaves the calling thread's current device as it found it
+// (a process that drives several GPUs from one thread must not have its later torch allocations land elsewhere).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) err = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define DEVICE_SCOPE(dev)      \
+  DeviceGuard _dev_guard(dev); \
+  CUDA_TRY(_dev_guard.err)
+
 // ---------------------------------------------------------------------------------------------- bf16 on the host
 uint16_t f2bf(float f) {
   uint32_t u;
@@ -173,7 +193,7 @@ void free_plan(Plan* p) {
   p->allocs.clear();
 }
 
-int alloc_act(Plan& pl, const std::string& name, int B, int H, int W, int C) {
+int alloc_act(Plan& pl, const std::string& name, int B, int H, int W, int C, cudaStream_t st) {
   Act a;
   a.B = B; a.H = H; a.W = W; a.C = C;
   a.plane = act_plane_elems(B, H, W, C);
@@ -181,10 +201,12 @@ int alloc_act(Plan& pl, const std::string& name, int B, int H, int W, int C) {
   const size_t bytes = a.plane * 2 * sizeof(__nv_bfloat16);
   cudaError_t e = cudaMalloc(&p, bytes);
   if (e != cudaSuccess) return fail(WSU_ERR_CUDA, "cudaMalloc(" + name + ", " + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
-  // borders that no producer writes (none today) and overhanging reads stay finite
-  cudaMemset(p, 0, bytes);
-  a.base = static_cast<__nv_bfloat16*>(p);
   pl.allocs.push_back(p);
+  // borders that no producer writes (none today) and overhanging reads stay finite. Zero-filled ON THE CALLER'S STREAM:
+  // the chain kernels run there, and a non-blocking stream does not order itself behind a legacy-stream memset.
+  e = cudaMemsetAsync(p, 0, bytes, st);
+  if (e != cudaSuccess) return fail(WSU_ERR_CUDA, "cudaMemsetAsync(" + name + "): " + cudaGetErrorString(e));
+  a.base = static_cast<__nv_bfloat16*>(p);
   pl.acts[name] = a;
   return WSU_OK;
 }
@@ -276,13 +298,13 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   return WSU_OK;
 }
 
-int build_plan_impl(wsu_context* h, int mb, int H, int W);
+int build_plan_impl(wsu_context* h, int mb, int H, int W, cudaStream_t st);
 
-int build_plan(wsu_context* h, int mb, int H, int W) {
+int build_plan(wsu_context* h, int mb, int H, int W, cudaStream_t st) {
   if (h->plan && h->plan->mb >= mb && h->plan->H == H && h->plan->W == W) return WSU_OK;
   if (h->plan) { cudaDeviceSynchronize(); free_plan(h->plan.get()); }
   h->plan.reset(new Plan());
-  const int rc = build_plan_impl(h, mb, H, W);
+  const int rc = build_plan_impl(h, mb, H, W, st);
   if (rc != WSU_OK) {  // never keep a half-built plan around
     free_plan(h->plan.get());
     h->plan.reset();
@@ -290,7 +312,7 @@ int build_plan(wsu_context* h, int mb, int H, int W) {
   return rc;
 }
 
-int build_plan_impl(wsu_context* h, int mb, int H, int W) {
+int build_plan_impl(wsu_context* h, int mb, int H, int W, cudaStream_t st) {
   Plan& pl = *h->plan;
   pl.mb = mb; pl.H = H; pl.W = W;
   const int n = h->nsteps;
@@ -298,20 +320,20 @@ int build_plan_impl(wsu_context* h, int mb, int H, int W) {
   // activations
   for (int l = 0; l <= n; ++l) {
     const int hh = H >> l, ww = W >> l;
-    if ((rc = alloc_act(pl, enc_name(l, 1), mb, hh, ww, chan(l)))) return rc;
+    if ((rc = alloc_act(pl, enc_name(l, 1), mb, hh, ww, chan(l), st))) return rc;
     if (!(n == 0)) {
-      if ((rc = alloc_act(pl, enc_name(l, 2), mb, hh, ww, chan(l)))) return rc;
+      if ((rc = alloc_act(pl, enc_name(l, 2), mb, hh, ww, chan(l), st))) return rc;
     }
     if (l < n) {
-      if ((rc = alloc_act(pl, "p" + std::to_string(l + 1), mb, hh / 2, ww / 2, chan(l)))) return rc;
+      if ((rc = alloc_act(pl, "p" + std::to_string(l + 1), mb, hh / 2, ww / 2, chan(l), st))) return rc;
     }
   }
   for (int l = n - 1; l >= 0; --l) {
     const int hh = H >> l, ww = W >> l;
-    if ((rc = alloc_act(pl, "u" + std::to_string(4 - l), mb, hh, ww, chan(l)))) return rc;
-    if ((rc = alloc_act(pl, dec_name(l, 1), mb, hh, ww, chan(l)))) return rc;
+    if ((rc = alloc_act(pl, "u" + std::to_string(4 - l), mb, hh, ww, chan(l), st))) return rc;
+    if ((rc = alloc_act(pl, dec_name(l, 1), mb, hh, ww, chan(l), st))) return rc;
     if (l > 0) {
-      if ((rc = alloc_act(pl, dec_name(l, 2), mb, hh, ww, chan(l)))) return rc;
+      if ((rc = alloc_act(pl, dec_name(l, 2), mb, hh, ww, chan(l), st))) return rc;
     }
   }
   // layer chain (first conv is launched separately)
@@ -465,11 +487,11 @@ int unet_ws_device(wsu_context* h, const void* img, int dtype, int B, int H, int
       return fail(WSU_ERR_INVALID, "local-variance weights exist only on the interior (crop=1), estimate.py:94-96");
     if (crop && (H < 3 || W < 3)) return fail(WSU_ERR_INVALID, "crop=1 needs H, W >= 3");
   }
-  CUDA_TRY(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h->device);
   if (!h->ev_chain) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chain, cudaEventDisableTiming));
   if (h->chain_pending && h->chain_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chain, 0));
   const int mb = pick_micro_batch(h, B, H, W);
-  if ((rc = build_plan(h, mb, H, W))) return rc;
+  if ((rc = build_plan(h, mb, H, W, st))) return rc;
   const size_t px = size_t(H) * W;
   const size_t esz = dtype == WSU_F32 ? 4 : 1;
   struct ChainDone {   // records the end of this call's work on every exit path
@@ -527,7 +549,7 @@ int wsu_create(wsu_handle* out, int device, int nsteps, int in_channels, int out
   if (e != cudaSuccess || ndev == 0)
     return fail(WSU_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libwsunet has no CPU fallback)");
   if (device < 0 || device >= ndev) return fail(WSU_ERR_INVALID, "device index out of range");
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   cudaDeviceProp prop;
   CUDA_TRY(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
@@ -551,7 +573,7 @@ int wsu_create(wsu_handle* out, int device, int nsteps, int in_channels, int out
 
 int wsu_destroy(wsu_handle h) {
   if (!h) return WSU_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   free_plan(h->plan.get());
   for (auto& kv : h->layers) { cudaFree(kv.second.wpack); cudaFree(kv.second.bias); cudaFree(kv.second.wres); }
@@ -715,7 +737,7 @@ static int upload_layer(wsu_context* h, const std::string& name, int cin, int co
 
 int wsu_commit_weights(wsu_handle h) {
   if (!h) return fail(WSU_ERR_INVALID, "null handle");
-  CUDA_TRY(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h->device);
   CUDA_TRY(cudaDeviceSynchronize());
   int rc;
   const int n = h->nsteps;
@@ -765,7 +787,7 @@ int wsu_unet_ws_estimate_host(wsu_handle h, const uint8_t* img_host, int B, int 
   if (!img_host || !beta_host) return fail(WSU_ERR_INVALID, "null host pointer");
   int rc = check_shape(h, B, H, W);
   if (rc) return rc;
-  CUDA_TRY(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h->device);
   const int mb = pick_micro_batch(h, B, H, W);
   const size_t px = size_t(H) * W;
   if (!h->s_copy) {
@@ -816,7 +838,7 @@ int wsu_filter_predict(int device, const void* img_dev, int img_dtype, int kind,
   int rc = filter_common_check(img_dev, img_dtype, kind, B, H, W);
   if (rc) return rc;
   if (!xhat_dev) return fail(WSU_ERR_INVALID, "null output pointer");
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partials = nullptr;
   const int strips = filter_ws_strips(H);
@@ -832,7 +854,7 @@ int wsu_filter_ws_estimate(int device, const void* img_dev, int img_dtype, int k
   if (rc) return rc;
   if (!beta_dev) return fail(WSU_ERR_INVALID, "null output pointer");
   if (weighted < -1 || weighted > 1) return fail(WSU_ERR_INVALID, "weighted must be -1, 0 or 1");
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partials = nullptr;
   int records = filter_ws_strips(H);
@@ -862,39 +884,85 @@ int wsu_filter_ws_estimate(int device, const void* img_dev, int img_dtype, int k
   return WSU_OK;
 }
 
+namespace {
+// Host-buffer path of the filter estimators: per (calling thread, device) two streams, a ring of three device staging
+// slots and a result buffer, all created once and reused by every call (no cudaMalloc / cudaFree on the call path:
+// allocating and unmapping a 2.6 GB batch buffer per call had capped this path at 18 GB/s of host-link traffic).
+struct HostPath {
+  static constexpr int kSlots = 3;
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t slot_free[kSlots] = {nullptr, nullptr, nullptr};
+  uint8_t* slot[kSlots] = {nullptr, nullptr, nullptr};
+  size_t slot_bytes = 0;
+  float* dout = nullptr;
+  size_t dout_n = 0;
+  ~HostPath() {   // thread exit: the context may already be gone, errors are ignored
+    for (int i = 0; i < kSlots; ++i) { if (slot[i]) cudaFree(slot[i]); if (slot_free[i]) cudaEventDestroy(slot_free[i]); }
+    if (dout) cudaFree(dout);
+    for (int i = 0; i < 2; ++i) if (s[i]) cudaStreamDestroy(s[i]);
+  }
+};
+thread_local std::map<int, HostPath> g_host_paths;   // keyed by device index
+
+int host_path_prepare(HostPath& hp, size_t slot_bytes, size_t n_out) {
+  for (int i = 0; i < 2; ++i)
+    if (!hp.s[i]) CUDA_TRY(cudaStreamCreateWithFlags(&hp.s[i], cudaStreamNonBlocking));
+  for (int i = 0; i < HostPath::kSlots; ++i)
+    if (!hp.slot_free[i]) CUDA_TRY(cudaEventCreateWithFlags(&hp.slot_free[i], cudaEventDisableTiming));
+  if (hp.slot_bytes < slot_bytes) {
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamSynchronize(hp.s[i]));
+    for (int i = 0; i < HostPath::kSlots; ++i) {
+      if (hp.slot[i]) { cudaFree(hp.slot[i]); hp.slot[i] = nullptr; }
+    }
+    hp.slot_bytes = 0;
+    for (int i = 0; i < HostPath::kSlots; ++i) CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&hp.slot[i]), slot_bytes));
+    hp.slot_bytes = slot_bytes;
+  }
+  if (hp.dout_n < n_out) {
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamSynchronize(hp.s[i]));
+    if (hp.dout) { cudaFree(hp.dout); hp.dout = nullptr; }
+    hp.dout_n = 0;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&hp.dout), n_out * sizeof(float)));
+    hp.dout_n = n_out;
+  }
+  return WSU_OK;
+}
+}  // namespace
+
 int wsu_filter_ws_estimate_host(int device, const uint8_t* img_host, int kind, int weighted, int clip, int correct_bias,
                                 float* beta_host, float* l1_host, int B, int H, int W) {
   if (!img_host || !beta_host) return fail(WSU_ERR_INVALID, "null host pointer");
-  CUDA_TRY(cudaSetDevice(device));
-  static thread_local cudaStream_t s[2] = {nullptr, nullptr};
-  if (!s[0]) {
-    CUDA_TRY(cudaStreamCreateWithFlags(&s[0], cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&s[1], cudaStreamNonBlocking));
-  }
-  const size_t px = size_t(H) * W;
-  // chunks alternate between two streams so the H2D copy of one overlaps the kernel of the other
-  const int chunk = std::max(1, std::min(B, int((size_t(64) << 20) / px)));
-  uint8_t* dimg = nullptr;
-  float* dout = nullptr;
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dimg), size_t(B) * px));
-  CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&dout), size_t(B) * 2 * 4));
-  int rc = WSU_OK, k = 0;
-  for (int b0 = 0; b0 < B && rc == WSU_OK; b0 += chunk, k ^= 1) {
-    const int n = std::min(chunk, B - b0);
-    cudaError_t e = cudaMemcpyAsync(dimg + size_t(b0) * px, img_host + size_t(b0) * px, size_t(n) * px, cudaMemcpyHostToDevice, s[k]);
-    if (e != cudaSuccess) { rc = fail(WSU_ERR_CUDA, cudaGetErrorString(e)); break; }
-    rc = wsu_filter_ws_estimate(device, dimg + size_t(b0) * px, WSU_U8, kind, weighted, clip, correct_bias, dout + b0,
-                                l1_host ? dout + B + b0 : nullptr, n, H, W, s[k]);
-    if (rc) break;
-    cudaMemcpyAsync(beta_host + b0, dout + b0, size_t(n) * 4, cudaMemcpyDeviceToHost, s[k]);
-    if (l1_host) cudaMemcpyAsync(l1_host + b0, dout + B + b0, size_t(n) * 4, cudaMemcpyDeviceToHost, s[k]);
-  }
-  cudaStreamSynchronize(s[0]);
-  cudaStreamSynchronize(s[1]);
-  cudaFree(dimg);
-  cudaFree(dout);
+  int rc = filter_common_check(img_host, WSU_U8, kind, B, H, W);
   if (rc) return rc;
-  CUDA_TRY(cudaGetLastError());
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(WSU_ERR_INVALID, "device index out of range");
+  DEVICE_SCOPE(device);
+  const size_t px = size_t(H) * W;
+  // chunks of <= 64 MB alternate between two streams and rotate through three staging slots: the H2D copy of chunk
+  // i+1 overlaps the kernels of chunk i; results stay on the device until one D2H copy at the end (a per-chunk copy
+  // into pageable host memory would block the host and serialise the pipeline)
+  const int chunk = std::max(1, std::min(B, int((size_t(64) << 20) / px)));
+  HostPath& hp = g_host_paths[device];
+  if ((rc = host_path_prepare(hp, size_t(chunk) * px, size_t(B) * 2))) return rc;
+  float* dout = hp.dout;
+  int i = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++i) {
+    const int n = std::min(chunk, B - b0), k = i & 1, sl = i % HostPath::kSlots;
+    cudaError_t e = cudaStreamWaitEvent(hp.s[k], hp.slot_free[sl], 0);   // the slot's previous kernel (other stream) is done
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(hp.slot[sl], img_host + size_t(b0) * px, size_t(n) * px, cudaMemcpyHostToDevice, hp.s[k]);
+    if (e != cudaSuccess) { rc = fail(WSU_ERR_CUDA, std::string("host staging: ") + cudaGetErrorString(e)); break; }
+    rc = wsu_filter_ws_estimate(device, hp.slot[sl], WSU_U8, kind, weighted, clip, correct_bias, dout + b0,
+                                l1_host ? dout + B + b0 : nullptr, n, H, W, hp.s[k]);
+    if (rc) break;
+    cudaEventRecord(hp.slot_free[sl], hp.s[k]);
+  }
+  cudaError_t e0 = cudaStreamSynchronize(hp.s[0]), e1 = cudaStreamSynchronize(hp.s[1]);
+  if (rc) return rc;
+  CUDA_TRY(e0);
+  CUDA_TRY(e1);
+  CUDA_TRY(cudaMemcpy(beta_host, dout, size_t(B) * 4, cudaMemcpyDeviceToHost));
+  if (l1_host) CUDA_TRY(cudaMemcpy(l1_host, dout + B, size_t(B) * 4, cudaMemcpyDeviceToHost));
   return WSU_OK;
 }
 
@@ -904,7 +972,7 @@ int wsu_ws_grad_prediction(int device, const void* img_dev, int img_dtype, const
   if (img_dtype != WSU_U8 && img_dtype != WSU_F32) return fail(WSU_ERR_INVALID, "dtype must be WSU_U8 or WSU_F32");
   if (crop < 0 || crop > 1) return fail(WSU_ERR_INVALID, "crop must be 0 or 1");
   if (B <= 0 || B > 65535 || H < 1 + 2 * crop || W < 1 + 2 * crop) return fail(WSU_ERR_INVALID, "need 1 <= B <= 65535 and a non-empty crop");
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   LAUNCH_TRY(launch_ws_grad_pred(img_dev, img_dtype == WSU_F32, coef_dev, grad_dev, B, H, W, crop, scale,
                                  static_cast<cudaStream_t>(stream)));
   return WSU_OK;
@@ -919,7 +987,7 @@ int wsu_ws_from_prediction(int device, const void* img_dev, int img_dtype, const
   if (weighted < -1 || weighted > 1) return fail(WSU_ERR_INVALID, "weighted must be -1, 0 or 1");
   if (weighted != 0 && !crop) return fail(WSU_ERR_INVALID, "local-variance weights exist only on the interior (crop=1)");
   if (xhat_cropped && !crop) return fail(WSU_ERR_INVALID, "cropped predictions need crop=1");
-  CUDA_TRY(cudaSetDevice(device));
+  DEVICE_SCOPE(device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int chunks = 32;
   float* partials = nullptr;
@@ -945,7 +1013,7 @@ int wsu_get_info(wsu_handle h, const char* key, int64_t* out) {
 int wsu_profile_read(wsu_handle h, float* ms_out, int cap) {
   if (!h || !ms_out) return fail(WSU_ERR_INVALID, "null argument");
   if (!h->profile || h->prof_n == 0 || int(h->prof_ev.size()) < h->prof_n + 1) return fail(WSU_ERR_STATE, "no profile recorded");
-  CUDA_TRY(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h->device);
   CUDA_TRY(cudaEventSynchronize(h->prof_ev[h->prof_n]));
   const int n = std::min(cap, h->prof_n);
   for (int i = 0; i < n; ++i) CUDA_TRY(cudaEventElapsedTime(&ms_out[i], h->prof_ev[i], h->prof_ev[i + 1]));
@@ -967,7 +1035,7 @@ int wsu_debug_layer(wsu_handle h, const char* name, float* dst_dev, size_t cap, 
   const int Ho = a.H + (with_halo ? 2 : 0), Wo = a.W + (with_halo ? 2 : 0);
   if (size_t(a.B) * a.C * Ho * Wo > cap) return fail(WSU_ERR_INVALID, "destination too small");
   if (dims_out) { dims_out[0] = a.B; dims_out[1] = a.C; dims_out[2] = Ho; dims_out[3] = Wo; }
-  CUDA_TRY(cudaSetDevice(h->device));
+  DEVICE_SCOPE(h->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (h->chain_pending && h->chain_stream != st) CUDA_TRY(cudaStreamWaitEvent(st, h->ev_chain, 0));
   LAUNCH_TRY(launch_unpack(a, dst_dev, with_halo, st));

@@ -49,3 +49,35 @@ def synthetic_stego_fast(n: int, alpha: float, H: int, W: int, device, seed: int
     mask = torch.rand(cover.shape, generator=g, device=device) < alpha
     bits = torch.randint(0, 2, cover.shape, generator=g, device=device, dtype=torch.uint8)
     return torch.where(mask, (cover & 0xFE) + bits, cover)
+
+
+GEN_CHUNK = 64   # images per generator chunk of synthetic_stego_chunk (shards are whole chunks)
+
+
+def synthetic_stego_chunk(chunk_index: int, alphas, H: int, W: int, device, chunk: int = GEN_CHUNK) -> torch.Tensor:
+    """Images [chunk_index*chunk, (chunk_index+1)*chunk) of the sharded synthetic workload (BASELINE.json configs[3]),
+    generated ON `device` from a generator seeded by the chunk index alone: whichever rank produces a chunk gets the same
+    bytes, so the vector gathered from N GPUs can be checked bit for bit against a single-GPU run. Same recipe as
+    synthetic_cover / embed_lsbr (different RNG stream); image g uses alpha = alphas[g % len(alphas)].
+    Returns (chunk,1,H,W) uint8 on `device`."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(COVER_SEED * 1000003 + int(chunk_index))
+    x = torch.rand(chunk, 1, H + 8, W + 8, generator=g, device=dev) * 255
+    k = torch.ones(1, 1, 5, 5, device=dev) / 25
+    x = torch.nn.functional.conv2d(torch.nn.functional.conv2d(x, k), k)
+    lo, hi = x.amin(dim=(1, 2, 3), keepdim=True), x.amax(dim=(1, 2, 3), keepdim=True)
+    x = (x - lo) / (hi - lo) * (247 - 8) + 8
+    x = x + torch.randn(x.shape, generator=g, device=dev) * 2
+    cover = x.round().clamp(0, 255).to(torch.uint8)
+    idx = torch.arange(chunk_index * chunk, (chunk_index + 1) * chunk, device=dev) % len(alphas)
+    a = torch.tensor(list(alphas), dtype=torch.float32, device=dev)[idx].view(chunk, 1, 1, 1)
+    mask = torch.rand(cover.shape, generator=g, device=dev) < a
+    bits = torch.randint(0, 2, cover.shape, generator=g, device=dev, dtype=torch.uint8)
+    return torch.where(mask, (cover & 0xFE) + bits, cover)
+
+
+def synthetic_stego_shard(first: int, n: int, alphas, H: int, W: int, device, chunk: int = GEN_CHUNK) -> torch.Tensor:
+    """Images [first, first+n) of the sharded workload; `first` and `n` must be multiples of `chunk`."""
+    if first % chunk or n % chunk:
+        raise ValueError(f'shards are whole generator chunks of {chunk} images')
+    return torch.cat([synthetic_stego_chunk(c, alphas, H, W, device, chunk) for c in range(first // chunk, (first + n) // chunk)])

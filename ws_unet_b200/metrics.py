@@ -99,32 +99,43 @@ class WSMeter:
 
 
 def produce_roc(df_ws: pd.DataFrame) -> pd.DataFrame:
-    """src/ws/roc.py:198-283 for WS estimators: per (stego_method, model_name) against the 'Cover' rows, thresholds
-    tau in linspace(0,1,501) on clip(beta_hat, 0), AUC by the reference's FPR-bin weighting, P_E = min (1-TPR+FPR)/2."""
+    """src/ws/roc.py:198-283: per (stego_method, model_name) against the 'Cover' rows, thresholds tau in
+    linspace(0,1,501) on clip(beta_hat, 0) (model names containing 'B0' use the detector's `score` column against alpha,
+    roc.py:211-213), AUC by the reference's FPR-bin weighting, P_E = min (1-TPR+FPR)/2.
+
+    `tpr_50` reproduces the reference as written: roc.py:251 divides TP(tau=.5) by TP(tau=.5) + FN where FN is the value
+    left over from the LAST threshold of the loop (tau = 0), i.e. the positives with beta_hat <= 0, not the positives with
+    beta_hat <= .5. Kept so that a results table regenerated through this package matches the reference's column."""
     out = []
     for (stego_method, model_name), _ in df_ws.groupby(['stego_method', 'model_name']):
         if stego_method == 'Cover':
             continue
         d = df_ws[(df_ws['model_name'] == model_name) & df_ws['stego_method'].isin([stego_method, 'Cover'])]
-        y_hat = np.clip(d['beta_hat'].to_numpy(), 0, None)
-        y = d['alpha'].to_numpy() / 2
+        if 'B0' in model_name:
+            y_hat = d['score'].to_numpy()
+            y = d['alpha'].to_numpy()
+        else:
+            y_hat = np.clip(d['beta_hat'].to_numpy(), 0, None)
+            y = d['alpha'].to_numpy() / 2
         taus = np.array(list(reversed(np.linspace(0, 1, 501, endpoint=True))))
         gt = y_hat[None, :] > taus[:, None]
         pos, neg = (y > 0.)[None, :], (y <= 0.)[None, :]
         TP, FP = (gt & pos).sum(1), (gt & neg).sum(1)
         TN, FN = (~gt & neg).sum(1), (~gt & pos).sum(1)
-        tpr, fpr = TP / (TP + FN), FP / (FP + TN)
-        bins = np.diff(fpr, prepend=fpr[0])
-        bins = bins / bins.sum()
-        auc = np.sum(bins * tpr)
-        err = (1 - tpr + fpr) / 2
-        i0 = int(np.argmin(err))
-        g50 = y_hat > .5
-        fpr50 = (g50 & (y <= 0.)).sum() / max(((y <= 0.)).sum(), 1)
-        tpr50 = (g50 & (y > 0.)).sum() / max(((y > 0.)).sum(), 1)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            tpr, fpr = TP / (TP + FN), FP / (FP + TN)
+            bins = np.diff(fpr, prepend=fpr[0])
+            bins = bins / bins.sum()
+            auc = np.sum(bins * tpr)
+            err = (1 - tpr + fpr) / 2
+            i0 = int(np.argmin(err))
+            g50 = y_hat > .5
+            TP50, FP50, TN50 = (g50 & (y > 0.)).sum(), (g50 & (y <= 0.)).sum(), (~g50 & (y <= 0.)).sum()
+            fpr50 = FP50 / (FP50 + TN50)
+            tpr50 = TP50 / (TP50 + FN[-1])          # roc.py:251: FN of the loop's last threshold (tau = 0)
         out.append(pd.DataFrame({
             'stego_method': stego_method, 'model_name': model_name, 'tau': taus, 'tpr': tpr, 'fpr': fpr, 'p_e': err[i0],
             'tau0': taus[i0], 'fpr_tau0': fpr[i0], 'tpr_tau0': tpr[i0], 'auc': auc, 'fpr_50': fpr50, 'tpr_50': tpr50,
-            'label': f'WS-{model_name}',
+            'label': model_name if 'B0' in model_name else f'WS-{model_name}',
         }))
     return pd.concat(out)

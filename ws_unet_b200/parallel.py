@@ -62,5 +62,9 @@ def estimate_sharded(n_total: int, load_images: typing.Callable[[int, int], torc
     outs = []
     for s in range(lo, hi, chunk):
         outs.append(estimate(load_images(s, min(hi, s + chunk))))
-    local = torch.cat(outs) if outs else torch.empty(0)
+    if outs:
+        local = torch.cat(outs)
+    else:   # world > n_total: this rank owns nothing, but it still takes part in the gather with the right device/dtype
+        dev = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+        local = torch.empty(0, dtype=torch.float32, device=dev)
     return gather_shards(local, n_total)

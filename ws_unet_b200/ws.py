@@ -42,6 +42,9 @@ def ws_estimate(images: torch.Tensor, predictor, weighted: int = 0, clip: bool =
     images: (B,1,H,W) uint8 pixels (or float32 in [0,1] as in WSLoss, src/_defs/losses.py:46-61).
     weighted: 1 -> 1/(5+var), -1 -> 5+var, 0 -> uniform (src/ws/estimate.py:93-110).
     clip: clip beta_hat at 0 (attack: True, predict_unet: False).  crop: 1 -> interior only, 0 -> whole image.
+    return_prediction: also return the predictor's output as the predictor itself defines it - a linear filter gives
+    pixel units on the 'valid' interior, (B,H-2,W-2) (filters/evaluate.py:136-140); a UNet gives its sigmoid output in
+    (0,1) on the whole image, (B,1,H,W) (unet.py:189; infere_single crops and scales it, evaluate.py:49-50).
     """
     images, dtype = _prep_images(images)
     B, _, H, W = images.shape
@@ -172,16 +175,24 @@ def attack(fname: str, channels: typing.List[int], pixel_estimator, mean_estimat
     if not np.array_equal(x0, np.round(x0)) or x0.min() < 0 or x0.max() > 255:
         raise ValueError("attack expects integer pixel values in 0..255")
     img = torch.from_numpy(x0.astype(np.uint8)).to(dev)[None, None]
+    # estimate.py:93,109: any `weighted` other than +-1 means uniform weights (abs(int(weighted)) == 1 selects the weighted arm)
+    w_mode = int(weighted) if abs(int(weighted)) == 1 else 0
     try:
         if isinstance(pixel_estimator, (str, UNet)):
-            beta = ws_estimate(img, pixel_estimator, weighted=int(weighted), clip=True, crop=1, correct_bias=correct_bias)
+            if isinstance(pixel_estimator, UNet) and tuple(img.shape[-2:]) != (512, 512):
+                # the reference's UNet estimator goes through CenterCrop(512) (src/unet/evaluate.py:46, loader.py:43-44):
+                # its 510x510 prediction does not broadcast against any other interior, the ValueError is caught below
+                # and the file is reported with beta_hat=None (estimate.py:115-118). Same here; the batched
+                # `ws_estimate` takes any H, W divisible by 2^nsteps.
+                raise ValueError(f'UNet pixel estimator expects 512x512 images, got {tuple(img.shape[-2:])}')
+            beta = ws_estimate(img, pixel_estimator, weighted=w_mode, clip=True, crop=1, correct_bias=correct_bias)
         else:
             x1_hat = torch.from_numpy(np.ascontiguousarray(pixel_estimator(xp)[..., 0], dtype=np.float32)).to(dev)[None]
             x_bias = None
             if correct_bias:
                 x_bar = process_image(x ^ 1) if process_image is not None else (x ^ 1)[..., channels].astype('float32')
                 x_bias = torch.from_numpy(np.ascontiguousarray(pixel_estimator(x_bar - xp)[..., 0], dtype=np.float32)).to(dev)[None]
-            beta = ws_from_prediction(img, x1_hat, weighted=int(weighted), clip=True, crop=1, x_bias=x_bias)
+            beta = ws_from_prediction(img, x1_hat, weighted=w_mode, clip=True, crop=1, x_bias=x_bias)
         beta_hat = np.float32(beta.item())
     except ValueError:
         beta_hat = None

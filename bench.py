@@ -478,11 +478,30 @@ def run_ours(args):
 
 
 def configure_precision(args, W, lib, h, model, imgs, dev):
-    """Every layer runs the three-term split-bf16 scheme (hi*hi + lo*hi + hi*lo, fp32 accumulation)."""
+    """Precision plan of the layers whose input lives at UNet level >= 1 (ws_unet_b200/unet/model.py::set_precision).
+    'auto' (default): UNet.calibrate_precision on 8 images of this rank's shard - the cheapest plan whose predictions stay
+    within 2e-4 px (max-abs over all pixels) of the three-term plan is used; the in-run `parity` block then checks the
+    chosen plan against the CPU reference like any other."""
     names = ['e12', 'e21', 'e22', 'e31', 'e32', 'upconv3', 'd31', 'd32', 'upconv4', 'd41', 'd42']
-    return {'dtype': 'bf16x3', 'terms_per_layer': {n: 3 for n in names},
-            'arithmetic': 'split-bf16 operands (hi + lo), 3 tcgen05 MMAs per MAC, fp32 accumulation in TMEM; integer WS arithmetic',
-            'report': {'mode': 'bf16x3'}}
+    deep = ['e21', 'e22', 'e31', 'e32', 'upconv3', 'd31', 'd32', 'upconv4']
+    if args.precision == 'auto':
+        report = model.calibrate_precision(imgs[:8], budget_px=2e-4)
+    else:
+        model.set_precision(args.precision)
+        report = {'chosen': model.active_precision(dev), 'requested': args.precision}
+    mode = model.active_precision(dev)
+    t = {'bf16x3': 3, 'fp16x2': 2, 'fp16x1': 1}[mode]
+    terms = {n: (t if n in deep else 3) for n in names}
+    if mode == 'bf16x3':
+        arith = 'split-bf16 operands (hi + lo), 3 tcgen05 MMAs per MAC, fp32 accumulation in TMEM; integer WS arithmetic'
+        dtype = 'bf16x3'
+    else:
+        arith = (f'full-resolution layers e12/d41/d42: split-bf16 operands, 3 tcgen05 MMAs per MAC; layers at level >= 1: one fp16 '
+                 f'activation plane x fp16 weights, {t} MMA(s) per MAC ({mode}, chosen by calibration against the 3-term plan); '
+                 'fp32 accumulation in TMEM; integer WS arithmetic')
+        dtype = f'bf16x3+{mode}'
+    report['mode'] = mode
+    return {'dtype': dtype, 'terms_per_layer': terms, 'arithmetic': arith, 'report': report}
 
 
 def main():
@@ -497,7 +516,7 @@ def main():
     ap.add_argument('--est-images', type=int, default=10000, help='images of the KB-filter estimator measurement (configs[1]); 0 skips it (launch lists of the UNet step)')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--size', type=int, default=512, help='image side; 1024 = BASELINE configs[4] (not the headline metric)')
-    ap.add_argument('--precision', default='auto', choices=['auto', 'bf16x3', 'mixed'])
+    ap.add_argument('--precision', default='auto', choices=['auto', 'bf16x3', 'fp16x2', 'fp16x1'])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

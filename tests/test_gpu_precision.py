@@ -1,0 +1,159 @@
+"""GPU (B200): the reduced-precision plans ('fp16x2' / 'fp16x1': the layers whose input lives at UNet level >= 1 read one
+fp16 activation plane with two / one MMA per MAC; e12, d41, d42 stay three-term split-bf16) against the oracle, the
+reference goldens at configuration size, and the calibration guard that decides whether a plan may be used.
+Bars are BASELINE.json's: predictions <= 1e-3 px max-abs, beta_hat <= 1e-4.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import unet_oracle as uo
+
+pytestmark = pytest.mark.gpu
+PX_TOL = 1e-3
+BETA_TOL = 1e-4
+MODES = ['fp16x2', 'fp16x1']
+
+
+def _model(nsteps, seed, dev, mode='bf16x3'):
+    import ws_unet_b200 as W
+    m = W.get_model(f'unet_{nsteps}', 1).to(dev)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in uo.numpy_weights(nsteps, seed=seed).items()})
+    return m.set_precision(mode)
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('nsteps,b,h,w', [(2, 1, 8, 8), (2, 3, 72, 40), (2, 2, 128, 200), (1, 5, 34, 66), (2, 2, 64, 1024)])
+def test_reduced_plans_match_oracle_ragged(cuda_dev, mode, nsteps, b, h, w):
+    sd = uo.numpy_weights(nsteps, seed=7)
+    m = _model(nsteps, 7, cuda_dev, mode)
+    assert m.active_precision(cuda_dev) == mode
+    x = np.random.default_rng(h * 1000 + w).random((b, 1, h, w), dtype=np.float32)
+    y = m(torch.from_numpy(x).to(cuda_dev)).cpu().numpy()
+    assert np.abs(y - uo.unet_forward(sd, x, nsteps)).max() * 255 < PX_TOL
+
+
+@pytest.mark.parametrize('mode', MODES)
+def test_reduced_plan_layers_and_halo(cuda_dev, mode):
+    """Every stored map under a reduced plan: level-0 maps keep split-bf16 accuracy, level >= 1 maps are ONE fp16 value
+    (relative 2^-11 of the map's own rounding, plus what the fp16 inputs of the producing layer cost); the reflect halo
+    is materialised in both formats."""
+    from ws_unet_b200 import _native
+    sd = uo.numpy_weights(2, seed=9)
+    m = _model(2, 9, cuda_dev, mode)
+    x = np.random.default_rng(3).random((2, 1, 48, 80), dtype=np.float32)
+    lib = _native.load()
+    m(torch.from_numpy(x).to(cuda_dev))
+    _, acts = uo.unet_forward(sd, x, 2, keep=True)
+    for name in ['e11', 'e12', 'p1', 'e21', 'e22', 'p2', 'e31', 'e32', 'u3', 'd31', 'd32', 'u4', 'd41']:
+        ref = acts[name]
+        if name in ('u3', 'u4'):   # stored WITHOUT the up-convolution's bias (folded into the consuming layer's bias)
+            ref = ref - sd[f'upconv{name[1]}.bias'][None, :, None, None]
+        ref_h = np.pad(ref, ((0, 0), (0, 0), (1, 1), (1, 1)), mode='reflect')
+        dims = (ctypes.c_int64 * 4)()
+        buf = torch.empty(ref_h.size, dtype=torch.float32, device=cuda_dev)
+        _native.check(lib.wsu_debug_layer(m._handle, name.encode(), ctypes.c_void_p(buf.data_ptr()), buf.numel(), 1, dims,
+                                          _native.stream_ptr(cuda_dev)))
+        got = buf.view(*ref_h.shape).cpu().numpy()
+        assert tuple(dims) == ref_h.shape
+        deep = name not in ('e11', 'e12', 'd41')
+        tol = (2e-3 if deep else 2e-5) * max(1.0, np.abs(acts[name]).max())
+        assert np.abs(got - ref_h).max() < tol, (name, np.abs(got - ref_h).max(), tol)
+        # halo == mirrored interior, exactly, in whatever format the map is stored
+        assert np.array_equal(got[:, :, 0, :], got[:, :, 2, :]) and np.array_equal(got[:, :, :, -1], got[:, :, :, -3]), name
+
+
+def test_unsupported_depths_stay_three_term(cuda_dev):
+    """unet_3 / unet_4 up-convolutions do not fit the shared-memory-resident kernel: the plan falls back and says so."""
+    m = _model(3, 5, cuda_dev)
+    x = torch.rand(1, 1, 32, 48, device=cuda_dev)
+    y0 = m(x)
+    m.set_precision('fp16x1')
+    assert m.active_precision(cuda_dev) == 'bf16x3'
+    assert torch.equal(m(x), y0)
+    m0 = _model(0, 5, cuda_dev, 'fp16x1')
+    assert m0.active_precision(cuda_dev) == 'bf16x3'
+    with pytest.raises(ValueError):
+        m.set_precision('fp8')
+
+
+@pytest.mark.parametrize('mode', MODES)
+def test_reduced_plan_ws_properties(cuda_dev, mode):
+    """Determinism, batch-position and micro-batch independence, host path == device path, switching plans back and forth."""
+    import ws_unet_b200 as W
+    from ws_unet_b200 import data as wdata
+    imgs = torch.stack([wdata.embed_lsbr(wdata.synthetic_cover(i, 96, 128), 0.4, i) for i in range(7)])[:, None]
+    d = imgs.to(cuda_dev)
+    m = _model(2, 41, cuda_dev)
+    b3 = W.ws_estimate(d, m, weighted=1, clip=False)
+    m.set_precision(mode)
+    b1, l1 = W.ws_estimate(d, m, weighted=1, clip=False, return_l1=True)
+    assert torch.equal(b1, W.ws_estimate(d, m, weighted=1, clip=False))
+    perm = torch.tensor([3, 0, 6, 2, 5, 1, 4], device=cuda_dev)
+    assert torch.equal(W.ws_estimate(d[perm], m, weighted=1, clip=False), b1[perm])
+    m.set_micro_batch(3, cuda_dev)
+    assert torch.equal(W.ws_estimate(d, m, weighted=1, clip=False), b1)
+    hb, hl = W.ws_estimate_host(imgs, m, weighted=1, clip=False, return_l1=True)
+    assert torch.equal(hb, b1.cpu()) and torch.equal(hl, l1.cpu())
+    m.set_micro_batch(0, cuda_dev)
+    assert (b1 - b3).abs().max().item() < BETA_TOL
+    m.set_precision('bf16x3')
+    assert torch.equal(W.ws_estimate(d, m, weighted=1, clip=False), b3)
+
+
+def test_calibration_accepts_and_rejects(cuda_dev, capsys):
+    """calibrate_precision keeps a reduced plan only when its predictions stay within the budget of the three-term plan.
+    Random-init weights (the benchmark's model) route almost nothing through the deep path -> the one-term plan passes; a
+    model whose up-convolution is scaled up so that the deep path dominates the output must be refused."""
+    import ws_unet_b200 as W
+    from ws_unet_b200 import data as wdata
+    imgs = torch.stack([wdata.embed_lsbr(wdata.synthetic_cover(i, 128, 128), 0.4, i) for i in range(4)])[:, None].to(cuda_dev)
+    torch.manual_seed(1234)
+    m = W.get_model('unet_2', 1).to(cuda_dev)
+    rep = m.calibrate_precision(imgs)
+    assert rep['chosen'] == 'fp16x1' and rep['max_abs_px']['fp16x1'] <= rep['budget_px']
+    assert m.active_precision(cuda_dev) == 'fp16x1'
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd['upconv4.weight'] *= 100.          # the decoder's deep input now carries the prediction (emulation: 3-5e-3 px)
+    sd['d32.weight'] *= 2.
+    m2 = W.get_model('unet_2', 1).to(cuda_dev)
+    m2.load_state_dict(sd)
+    rep2 = m2.calibrate_precision(imgs)
+    with capsys.disabled():
+        print(f'\n[calibration] random init: {rep["max_abs_px"]} -> {rep["chosen"]}; deep-path-heavy weights: {rep2["max_abs_px"]} -> {rep2["chosen"]}')
+    assert rep2['chosen'] == 'bf16x3' and m2.active_precision(cuda_dev) == 'bf16x3'
+    assert rep2['max_abs_px']['fp16x1'] > rep2['budget_px']
+
+
+@pytest.mark.parametrize('mode', MODES)
+def test_reduced_plans_config1_and_config5_against_reference_goldens(cuda_dev, mode, capsys):
+    """BASELINE.json configs[0] (64 x 512^2, alpha = 0.4) and one 1024^2 image (configs[4]) under the reduced plans, against
+    the unmodified reference's predict_unet values and prediction grids (tests/golden/config_golden.npz)."""
+    import ws_unet_b200 as W
+    from ws_unet_b200 import data as wdata
+    g = dict(np.load(GOLDEN / 'config_golden.npz'))
+    torch.manual_seed(1234)
+    m = W.get_model('unet_2', in_channels=1, out_channels=1, channel=[0], drop_rate=0.).to(cuda_dev).set_precision(mode)
+    imgs = torch.stack([wdata.embed_lsbr(wdata.synthetic_cover(i), 0.4, i) for i in range(64)])[:, None].to(cuda_dev)
+    beta, l1, yhat = W.ws_estimate(imgs, m, weighted=0, clip=False, crop=1, return_l1=True, return_prediction=True)
+    d_beta = np.abs(beta.cpu().numpy().astype(np.float64) - g['cfg1_beta_l1'][:, 0]).max()
+    d_l1 = np.abs(l1.cpu().numpy().astype(np.float64) - g['cfg1_beta_l1'][:, 1]).max()
+    xhat = (yhat[:, 0, 1:-1, 1:-1] * 255.).cpu().numpy()
+    d_px = max(np.abs(xhat[i][::3, ::3] - g[f'cfg1_xhat_sub3_{i}']).max() for i in (0, 37))
+    m.set_precision('bf16x3')
+    y3 = m(imgs)
+    d_plan = ((yhat - y3).abs().max() * 255).item()     # every pixel of all 64 images against the three-term plan
+    m.set_precision(mode)
+    st = wdata.embed_lsbr(wdata.synthetic_cover(5000, 1024, 1024), 0.4, 5000)[None, None].to(cuda_dev)
+    y = m(st)
+    d5 = np.abs(y[0, 0, ::5, ::5].cpu().numpy() - g['cfg5_y_sub5']).max() * 255
+    b5 = W.ws_estimate(st, m, weighted=0, clip=False, crop=1)
+    d5b = abs(b5.item() - g['cfg5_beta_l1'][0])
+    with capsys.disabled():
+        print(f'\n[{mode}] config 1: max|x_hat - ref grid| = {d_px:.3e} px, max|x_hat - three-term plan| = {d_plan:.3e} px (all pixels), '
+              f'max|beta_hat - ref| = {d_beta:.3e}, max|l1 - ref| = {d_l1:.3e}; config 5: {d5:.3e} px, |beta_hat - ref| = {d5b:.3e}')
+    assert d_px < PX_TOL and d_plan + 5e-5 < PX_TOL and d_beta < BETA_TOL and d_l1 < 1e-3
+    assert d5 < PX_TOL and d5b < BETA_TOL

@@ -63,6 +63,8 @@ def conv3(x, w, b, mode):
         ah, al = split_bf16(xp)
         wq = fp16(w)
         y = F.conv2d(ah, wq) + F.conv2d(al, wq)
+    elif mode == 'a16w16':
+        y = F.conv2d(fp16(xp), fp16(w))
     else:
         raise ValueError(mode)
     return f32(f32(y) + b.view(1, -1, 1, 1))
@@ -75,11 +77,20 @@ def upconv(x, w, b, mode):
         a = fp16(x)
         wh, wl = split_fp16(w)
         y = F.conv_transpose2d(a, wh, stride=2) + F.conv_transpose2d(a, wl, stride=2)
+    elif mode == 'a16w16':
+        y = F.conv_transpose2d(fp16(x), fp16(w), stride=2)
     else:
         ah, al = split_bf16(x)
         wh, wl = split_bf16(w)
         y = F.conv_transpose2d(ah, wh, stride=2) + F.conv_transpose2d(al, wh, stride=2) + F.conv_transpose2d(ah, wl, stride=2)
     return f32(f32(y) + b.view(1, -1, 1, 1))
+
+
+def conv3_cat(up, skip, w, b, mode_up, mode_skip):
+    """3x3 conv over cat([up, skip]) with a precision mode per concat source (bias added once)"""
+    c = up.shape[1]
+    z = torch.zeros_like(b)
+    return f32(conv3(up, w[:, :c], z, mode_up) + conv3(skip, w[:, c:], z, mode_skip) + b.view(1, -1, 1, 1))
 
 
 def forward(sd, x, modes):
@@ -95,7 +106,10 @@ def forward(sd, x, modes):
     e32 = c3('e32', e31)
     d31 = c3('d31', torch.cat([upconv(e32, *g('upconv3'), m('upconv3')), e22], 1))
     d32 = c3('d32', d31)
-    d41 = c3('d41', torch.cat([upconv(d32, *g('upconv4'), m('upconv4')), e12], 1))
+    if 'd41.up' in modes:
+        d41 = F.relu(conv3_cat(upconv(d32, *g('upconv4'), m('upconv4')), e12, *g('d41'), modes['d41.up'], m('d41')))
+    else:
+        d41 = c3('d41', torch.cat([upconv(d32, *g('upconv4'), m('upconv4')), e12], 1))
     d42 = c3('d42', d41)
     z = F.conv2d(d42, *g('outconv'))
     return torch.sigmoid(z) * 255.

@@ -1,6 +1,7 @@
 // C ABI of libwsunet (include/wsunet.h): handle, weight packing, per-shape plan (buffers + TMA tensor maps),
 // layer chain of UNet.forward (src/unet/model/unet.py:137-189) and the fused / stand-alone WS estimators.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -76,6 +77,16 @@ float bf2f(uint16_t h) {
   std::memcpy(&f, &u, 4);
   return f;
 }
+// fp16 on the host (round to nearest even through the toolkit's own conversion)
+uint16_t f2h(float f) {
+  const __half_raw r = __half_raw(__float2half_rn(f));
+  return r.x;
+}
+float h2f(uint16_t v) {
+  __half_raw r;
+  r.x = v;
+  return __half2float(__half(r));
+}
 inline size_t sw128_off(int row, int k) {  // byte offset of bf16 element (row, k) inside a K-major SWIZZLE_128B tile
   return size_t(row) * 128 + size_t(((k >> 3) ^ (row & 7)) << 4) + size_t(k & 7) * 2;
 }
@@ -101,13 +112,30 @@ int make_act_tmap(CUtensorMap* m, const Act& a, int TW, int TH) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(WSU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t Wp = a.W + 2, Hp = a.H + 2;
-  cuuint64_t dims[5] = {cuuint64_t(a.C), Wp, Hp, cuuint64_t(a.B), 2};
+  const cuuint32_t planes = a.fmt == ACT_F16 ? 1 : 2;   // 2-byte elements either way (bf16 pair or one fp16 plane)
+  cuuint64_t dims[5] = {cuuint64_t(a.C), Wp, Hp, cuuint64_t(a.B), planes};
   cuuint64_t strides[4] = {cuuint64_t(a.C) * 2, Wp * a.C * 2, Hp * Wp * a.C * 2, cuuint64_t(a.plane) * 2};
-  cuuint32_t box[5] = {64, cuuint32_t(TW), cuuint32_t(TH), 1, 2};
+  cuuint32_t box[5] = {64, cuuint32_t(TW), cuuint32_t(TH), 1, planes};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, a.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(WSU_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(int(r)));
+  return WSU_OK;
+}
+
+// 2-D map over a layer's packed weights seen as rows of 128 B (64 two-byte elements): box = 64 rows = one CTA's half of a
+// 128-row tile. No swizzle: the tiles are stored in the order the tensor core reads them.
+int make_w_tmap(CUtensorMap* m, const void* wpack, size_t bytes) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(WSU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {64, cuuint64_t(bytes / 128)};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpack), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(WSU_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed with code " + std::to_string(int(r)));
   return WSU_OK;
 }
 
@@ -121,6 +149,11 @@ struct LayerW {  // device-side packed weights of one tensor-core layer
   uint8_t* wpack = nullptr;
   float* bias = nullptr;
   int cin = 0, cout = 0, n_tile = 0, ntaps = 0, npos = 0;
+  int terms = 3;            // MMAs per MAC: 3 = split-bf16 weights against split-bf16 inputs; 2 / 1 = fp16 (hi, lo) / hi weights
+                            // against ONE fp16 input plane (precision plan, see wsu_context::precision)
+  size_t wpack_bytes = 0;
+  int f16_cblocks0 = 0;     // decoder layer at level 0 under a reduced plan: its first channel blocks (the up-convolution's
+                            // output) are fp16 pairs against ONE fp16 plane, the skip half stays three-term
   uint8_t* wres = nullptr;  // transposed conv only: phase-stacked tiles for the resident-weight kernel (may stay null)
   int res_ntile = 0, res_cot = 0;
 };
@@ -176,6 +209,13 @@ struct wsu_context {
   int dbg = 0;            // env WSU_DBG: knock-out switches for timing experiments (results are wrong when set)
   int a_collector = 1;    // option "a_collector" (default on, +0.4 % measured): Cout >= 128 layers reuse A_hi from the A collector (hi*hi, hi*lo, lo*hi order)
   int l2_prefetch = 0;    // halo kernels prefetch the next item's boxes into L2 (option "l2_prefetch"); measured 1 % slower
+  // Precision plan (option "precision"). 0: every layer three-term split-bf16 (16 significand bits per operand; 2e-5 px).
+  // 1 / 2: the layers whose INPUT lives at level >= 1 of the UNet (e21.., d3x, up-convolutions) read one fp16 plane against
+  // fp16 (hi, lo) / fp16 hi-only weights = 2 / 1 MMAs per MAC and half the activation bytes; the full-resolution layers
+  // (e12, d41, d42), whose rounding reaches the output directly, stay three-term. Whether a plan keeps a given model inside
+  // the 1e-3 px bar depends on its weights: UNet.calibrate_precision() measures it against plan 0 and picks.
+  int precision = 0;
+  int precision_active = 0;   // what commit could honour (needs resident up-convolutions: unet_1, unet_2)
   bool use_upres = true;  // transposed convs through upconv_res_kernel (option "upconv_resident")
   bool use_halo = true;  // 3x3 layers through conv_halo_kernel (option "halo"; 0 = per-tap reload kernel, for A/B runs)
 };
@@ -193,12 +233,13 @@ void free_plan(Plan* p) {
   p->allocs.clear();
 }
 
-int alloc_act(Plan& pl, const std::string& name, int B, int H, int W, int C, cudaStream_t st) {
+int alloc_act(Plan& pl, const std::string& name, int B, int H, int W, int C, int fmt, cudaStream_t st) {
   Act a;
   a.B = B; a.H = H; a.W = W; a.C = C;
+  a.fmt = fmt;
   a.plane = act_plane_elems(B, H, W, C);
   void* p = nullptr;
-  const size_t bytes = a.plane * 2 * sizeof(__nv_bfloat16);
+  const size_t bytes = a.plane * (fmt == ACT_F16 ? 1 : 2) * sizeof(__nv_bfloat16);
   cudaError_t e = cudaMalloc(&p, bytes);
   if (e != cudaSuccess) return fail(WSU_ERR_CUDA, "cudaMalloc(" + name + ", " + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
   pl.allocs.push_back(p);
@@ -211,18 +252,18 @@ int alloc_act(Plan& pl, const std::string& name, int B, int H, int W, int C, cud
   return WSU_OK;
 }
 
-size_t per_image_bytes(int nsteps, int H, int W) {
+size_t per_image_bytes(int nsteps, int H, int W, bool deep_f16) {
   size_t total = 0;
-  auto add = [&](int l, int c) { total += size_t(H >> l) * (W >> l) * c * 4; };
+  auto add = [&](int l, int c, bool f16) { total += size_t(H >> l) * (W >> l) * c * (f16 ? 2 : 4); };
   for (int l = 0; l <= nsteps; ++l) {
-    add(l, chan(l));
-    add(l, chan(l));
-    if (l < nsteps) add(l + 1, chan(l));
+    add(l, chan(l), deep_f16 && l >= 1);
+    add(l, chan(l), deep_f16 && l >= 1);
+    if (l < nsteps) add(l + 1, chan(l), deep_f16);
   }
   for (int l = nsteps - 1; l >= 0; --l) {
-    add(l, chan(l));
-    add(l, chan(l));
-    add(l, chan(l));
+    add(l, chan(l), deep_f16);               // up-convolution output
+    add(l, chan(l), deep_f16 && l >= 1);
+    if (l > 0) add(l, chan(l), deep_f16);
   }
   return total + total / 8;
 }
@@ -231,7 +272,7 @@ size_t per_image_bytes(int nsteps, int H, int W) {
 int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& lw, const Act& src0, const Act* src1, const Act* out, const Act* pool,
              bool upsample, bool relu, int epi) {
   ConvParams p;
-  std::memset(&p, 0, sizeof(p));
+  std::memset(static_cast<void*>(&p), 0, sizeof(p));
   const int TW = 16, TH = 8;
   const int m_sub = 256 / lw.n_tile;
   int rc = make_act_tmap(&p.tmapA0, src0, TW, TH);
@@ -243,6 +284,7 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   rc = make_act_tmap(&p.tmapH1, src1 ? *src1 : src0, kHaloTW + 2, kHaloTH + 2);
   if (rc) return rc;
   p.wpack = lw.wpack;
+  if ((rc = make_w_tmap(&p.tmapW, lw.wpack, lw.wpack_bytes))) return rc;
   p.bias = lw.bias;
   p.cblocks0 = src0.C / 64;
   p.cblocks = lw.cin / 64;
@@ -252,6 +294,14 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
     p.tap_dy[t] = (lw.ntaps == 9) ? t / 3 : 1;
   }
   p.npos = lw.npos;
+  p.terms = lw.terms;
+  p.src0_f16 = lw.f16_cblocks0 > 0;
+  {
+    const bool in0_f16 = src0.fmt == ACT_F16, in1_f16 = src1 ? src1->fmt == ACT_F16 : in0_f16;
+    const bool ok = p.src0_f16 ? (lw.terms == 3 && in0_f16 && !in1_f16 && lw.f16_cblocks0 == src0.C / 64 && lw.n_tile == 64)
+                               : ((lw.terms != 3) == in0_f16 && in1_f16 == in0_f16);
+    if (!ok) return fail(WSU_ERR_STATE, "internal: layer " + lname + " and its input maps disagree about the precision plan");
+  }
   p.n_tiles = lw.cout / lw.n_tile;
   p.cout = lw.cout;
   p.B = src0.B; p.H = src0.H; p.W = src0.W;
@@ -278,12 +328,13 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   int ui = -1;
   if (upsample && lw.wres && out) {
     UpconvParams u;
-    std::memset(&u, 0, sizeof(u));
+    std::memset(static_cast<void*>(&u), 0, sizeof(u));
     rc = make_act_tmap(&u.tmapA, src0, 16, 8);
     if (rc) return rc;
     u.wres = lw.wres;
     u.bias = lw.bias;
     u.cblocks = lw.cin / 64;
+    u.terms = lw.terms;
     u.co_t = lw.res_cot;
     u.n_tiles = lw.cout / lw.res_cot;
     u.B = src0.B; u.H = src0.H; u.W = src0.W;
@@ -317,23 +368,28 @@ int build_plan_impl(wsu_context* h, int mb, int H, int W, cudaStream_t st) {
   pl.mb = mb; pl.H = H; pl.W = W;
   const int n = h->nsteps;
   int rc;
-  // activations
+  // activations. Under a reduced-precision plan every map at level >= 1 (and every up-convolution output) is read only by
+  // one-/two-term layers or channel blocks and is stored as ONE fp16 plane; e11, e12, d41 feed three-term layers and stay
+  // split-bf16.
+  auto fmt_at = [&](int level) { return (h->precision_active != 0 && level >= 1) ? int(ACT_F16) : int(ACT_SPLIT); };
   for (int l = 0; l <= n; ++l) {
     const int hh = H >> l, ww = W >> l;
-    if ((rc = alloc_act(pl, enc_name(l, 1), mb, hh, ww, chan(l), st))) return rc;
+    if ((rc = alloc_act(pl, enc_name(l, 1), mb, hh, ww, chan(l), fmt_at(l), st))) return rc;
     if (!(n == 0)) {
-      if ((rc = alloc_act(pl, enc_name(l, 2), mb, hh, ww, chan(l), st))) return rc;
+      if ((rc = alloc_act(pl, enc_name(l, 2), mb, hh, ww, chan(l), fmt_at(l), st))) return rc;
     }
     if (l < n) {
-      if ((rc = alloc_act(pl, "p" + std::to_string(l + 1), mb, hh / 2, ww / 2, chan(l), st))) return rc;
+      if ((rc = alloc_act(pl, "p" + std::to_string(l + 1), mb, hh / 2, ww / 2, chan(l), fmt_at(l + 1), st))) return rc;
     }
   }
   for (int l = n - 1; l >= 0; --l) {
     const int hh = H >> l, ww = W >> l;
-    if ((rc = alloc_act(pl, "u" + std::to_string(4 - l), mb, hh, ww, chan(l), st))) return rc;
-    if ((rc = alloc_act(pl, dec_name(l, 1), mb, hh, ww, chan(l), st))) return rc;
+    // up-convolution outputs are fp16 at every level (u4 feeds d41's two-term source-0 blocks); their bias is folded
+    // into the consuming layer's bias at commit, which keeps the stored values small and their rounding harmless
+    if ((rc = alloc_act(pl, "u" + std::to_string(4 - l), mb, hh, ww, chan(l), fmt_at(l + 1), st))) return rc;
+    if ((rc = alloc_act(pl, dec_name(l, 1), mb, hh, ww, chan(l), fmt_at(l), st))) return rc;
     if (l > 0) {
-      if ((rc = alloc_act(pl, dec_name(l, 2), mb, hh, ww, chan(l), st))) return rc;
+      if ((rc = alloc_act(pl, dec_name(l, 2), mb, hh, ww, chan(l), fmt_at(l), st))) return rc;
     }
   }
   // layer chain (first conv is launched separately)
@@ -390,7 +446,7 @@ int check_shape(wsu_context* h, int B, int H, int W) {
 int pick_micro_batch(wsu_context* h, int B, int H, int W) {
   if (h->micro_batch > 0) return int(std::min<int64_t>(h->micro_batch, B));
   const size_t budget = size_t(20) << 30;
-  int mb = int(std::max<size_t>(1, budget / per_image_bytes(h->nsteps, H, W)));
+  int mb = int(std::max<size_t>(1, budget / per_image_bytes(h->nsteps, H, W, h->precision_active != 0)));
   mb = std::min(std::min(mb, 64), B);
   // even passes: avoid a short ragged tail pass (e.g. B=256 -> 8 x 32 instead of 7 x 33 + 25)
   const int passes = (B + mb - 1) / mb;
@@ -457,11 +513,13 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
       p.crop = crop;
     }
     mark(i + 1);
-    if (pl.up_idx[i] >= 0 && h->use_upres) {
+    if (p.src0_f16) {
+      LAUNCH_TRY(launch_conv_halo(p, n_tile, epi, h->num_sms, st));
+    } else if (pl.up_idx[i] >= 0 && (h->use_upres || p.terms != 3)) {
       UpconvParams u = pl.ups[pl.up_idx[i]];
       if (nimg != pl.mb) { u.B = nimg; u.total_boxes = nimg * u.tiles_x * u.tiles_y; }
       LAUNCH_TRY(launch_upconv_res(u, 4 * u.co_t, h->num_sms, st));
-    } else if (halo && (h->use_pair == 2 || (h->use_pair == 1 && n_tile == 128))) {
+    } else if (p.ntaps == 9 && (p.terms != 3 || (halo && (h->use_pair == 2 || (h->use_pair == 1 && n_tile == 128))))) {
       p.total_items = ((p.total_sub + 3) / 4) * p.n_tiles;   // pair items: 2 slots x 2 CTAs = 4 boxes
       LAUNCH_TRY(launch_conv_halo2(p, n_tile, epi, h->num_sms, st));
     } else if (halo)
@@ -567,6 +625,7 @@ int wsu_create(wsu_handle* out, int device, int nsteps, int in_channels, int out
   if (const char* e = std::getenv("WSU_HALO")) h->use_halo = std::atoi(e) != 0;
   if (const char* e = std::getenv("WSU_A_COLLECTOR")) h->a_collector = std::atoi(e) != 0;
   if (const char* e = std::getenv("WSU_DBG")) h->dbg = std::atoi(e);
+  if (const char* e = std::getenv("WSU_PRECISION")) h->precision = std::max(0, std::min(2, std::atoi(e)));
   *out = h;
   return WSU_OK;
 }
@@ -624,6 +683,14 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
     h->use_halo = value != 0;
     return WSU_OK;
   }
+  if (!std::strcmp(key, "precision")) {
+    if (value < 0 || value > 2) return fail(WSU_ERR_INVALID, "precision must be 0 (three-term), 1 (two-term deep layers) or 2 (one-term deep layers)");
+    if (h->precision != int(value)) {
+      h->precision = int(value);
+      if (h->committed) return wsu_commit_weights(h);   // weights are packed per plan (bf16 or fp16 pairs); drops the shape plan too
+    }
+    return WSU_OK;
+  }
   if (!std::strcmp(key, "profile")) {
     h->profile = value != 0;
     return WSU_OK;
@@ -660,7 +727,10 @@ static int expect_dims(wsu_context* h, const std::string& name, std::vector<int6
   return WSU_OK;
 }
 
-static int upload_layer(wsu_context* h, const std::string& name, int cin, int cout, bool transposed) {
+// f16_cblocks0: leading 64-channel blocks packed as fp16 pairs although the layer is three-term (decoder source 0);
+// bias_override: bias to upload instead of the state_dict's (up-convolution bias folded away / folded in)
+static int upload_layer(wsu_context* h, const std::string& name, int cin, int cout, bool transposed, int terms,
+                        int f16_cblocks0 = 0, const std::vector<float>* bias_override = nullptr) {
   const HostTensor *w, *b;
   int rc;
   if (transposed) {
@@ -671,6 +741,13 @@ static int upload_layer(wsu_context* h, const std::string& name, int cin, int co
   if ((rc = expect_dims(h, name + ".bias", {cout}, &b))) return rc;
   LayerW lw;
   lw.cin = cin; lw.cout = cout;
+  lw.terms = terms;
+  lw.f16_cblocks0 = f16_cblocks0;
+  // (hi, lo) pair of one weight in its channel block's operand type: bf16 for the three-term scheme, fp16 under a reduced plan
+  auto split16 = [terms, f16_cblocks0](float v, int cblock, uint16_t& vh, uint16_t& vl) {
+    if (terms == 3 && cblock >= f16_cblocks0) { vh = f2bf(v); vl = f2bf(v - bf2f(vh)); }
+    else { vh = f2h(v); vl = f2h(v - h2f(vh)); }
+  };
   lw.n_tile = cout == 64 ? 64 : 128;
   lw.ntaps = transposed ? 1 : 9;
   lw.npos = transposed ? 4 : 1;
@@ -691,8 +768,8 @@ static int upload_layer(wsu_context* h, const std::string& name, int cin, int co
                 v = w->data[((size_t(ci) * cout + co) * 2 + (pos >> 1)) * 2 + (pos & 1)];
               else
                 v = w->data[((size_t(co) * cin + ci) * 3 + tap / 3) * 3 + tap % 3];
-              const uint16_t vh = f2bf(v);
-              const uint16_t vl = f2bf(v - bf2f(vh));
+              uint16_t vh, vl;
+              split16(v, c, vh, vl);
               std::memcpy(hi + sw128_off(n, k), &vh, 2);
               std::memcpy(lo + sw128_off(n, k), &vl, 2);
             }
@@ -715,8 +792,8 @@ static int upload_layer(wsu_context* h, const std::string& name, int cin, int co
             for (int k = 0; k < 64; ++k) {
               const int pos = r / lw.res_cot, co = nt * lw.res_cot + r % lw.res_cot, ci = c * 64 + k;
               const float v = w->data[((size_t(ci) * cout + co) * 2 + (pos >> 1)) * 2 + (pos & 1)];
-              const uint16_t vh = f2bf(v);
-              const uint16_t vl = f2bf(v - bf2f(vh));
+              uint16_t vh, vl;
+              split16(v, c, vh, vl);
               std::memcpy(hi + sw128_off(r, k), &vh, 2);
               std::memcpy(lo + sw128_off(r, k), &vl, 2);
             }
@@ -727,10 +804,11 @@ static int upload_layer(wsu_context* h, const std::string& name, int cin, int co
   }
   auto old = h->layers.find(name);
   if (old != h->layers.end()) { cudaFree(old->second.wpack); cudaFree(old->second.bias); cudaFree(old->second.wres); }
+  lw.wpack_bytes = pack.size();
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&lw.wpack), pack.size()));
   CUDA_TRY(cudaMemcpy(lw.wpack, pack.data(), pack.size(), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&lw.bias), size_t(cout) * 4));
-  CUDA_TRY(cudaMemcpy(lw.bias, b->data.data(), size_t(cout) * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(lw.bias, bias_override ? bias_override->data() : b->data.data(), size_t(cout) * 4, cudaMemcpyHostToDevice));
   h->layers[name] = lw;
   return WSU_OK;
 }
@@ -751,14 +829,52 @@ int wsu_commit_weights(wsu_handle h) {
   CUDA_TRY(cudaMemcpy(h->e11_w, w->data.data(), w->data.size() * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->e11_b), 64 * 4));
   CUDA_TRY(cudaMemcpy(h->e11_b, b->data.data(), 64 * 4, cudaMemcpyHostToDevice));
+  // A reduced-precision plan needs every up-convolution's weight set resident in shared memory (upconv_res_kernel is the
+  // only fp16-input transposed convolution): 64 * N_TILE * cblocks * 4 B <= 128 KB, i.e. unet_1 and unet_2.
+  h->precision_active = h->precision;
+  for (int l = n - 1; l >= 0 && h->precision_active; --l) {
+    const int cb = chan(l + 1) / 64;
+    bool fits = false;
+    for (int cot : {64, 32}) fits = fits || (chan(l) % cot == 0 && cb * 4 * cot * 256 <= kUpconvResBytes);
+    if (!fits) h->precision_active = 0;
+  }
+  if (n == 0) h->precision_active = 0;
+  const int deep_terms = h->precision_active == 2 ? 1 : h->precision_active == 1 ? 2 : 3;
+  auto terms_at = [&](int input_level) { return input_level >= 1 ? deep_terms : 3; };
   for (int l = 0; l <= n; ++l) {
-    if (l > 0 && (rc = upload_layer(h, enc_name(l, 1), chan(l - 1), chan(l), false))) return rc;
-    if ((rc = upload_layer(h, enc_name(l, 2), chan(l), chan(l), false))) return rc;
+    if (l > 0 && (rc = upload_layer(h, enc_name(l, 1), chan(l - 1), chan(l), false, terms_at(l)))) return rc;
+    if ((rc = upload_layer(h, enc_name(l, 2), chan(l), chan(l), false, terms_at(l)))) return rc;
   }
   for (int l = n - 1; l >= 0; --l) {
-    if ((rc = upload_layer(h, up_name(l), chan(l + 1), chan(l), true))) return rc;
-    if ((rc = upload_layer(h, dec_name(l, 1), 2 * chan(l), chan(l), false))) return rc;
-    if ((rc = upload_layer(h, dec_name(l, 2), chan(l), chan(l), false))) return rc;
+    if (!h->precision_active) {
+      if ((rc = upload_layer(h, up_name(l), chan(l + 1), chan(l), true, 3))) return rc;
+      if ((rc = upload_layer(h, dec_name(l, 1), 2 * chan(l), chan(l), false, 3))) return rc;
+    } else {
+      // The up-convolution's output is stored as one fp16 plane. Its bias b_up is a per-channel constant, and the reflect
+      // padding of a constant is that constant, so conv3x3(cat[u + b_up, skip]) = conv3x3(cat[u, skip]) + sum_{ci,tap}
+      // W[co][ci][tap] * b_up[ci] exactly: the up-convolution stores u WITHOUT its bias (small values, small absolute
+      // rounding) and the consuming layer's bias absorbs the constant (computed in double).
+      const int cu = chan(l), co = chan(l);
+      const HostTensor *wd, *bd, *bu;
+      if ((rc = expect_dims(h, dec_name(l, 1) + ".weight", {co, 2 * cu, 3, 3}, &wd))) return rc;
+      if ((rc = expect_dims(h, dec_name(l, 1) + ".bias", {co}, &bd))) return rc;
+      if ((rc = expect_dims(h, up_name(l) + ".bias", {cu}, &bu))) return rc;
+      std::vector<float> zero(size_t(cu), 0.f), folded(size_t(co), 0.f);
+      for (int o = 0; o < co; ++o) {
+        double acc = bd->data[o];
+        for (int ci = 0; ci < cu; ++ci) {
+          double ws = 0;
+          for (int t = 0; t < 9; ++t) ws += wd->data[(size_t(o) * 2 * cu + ci) * 9 + t];
+          acc += ws * double(bu->data[ci]);
+        }
+        folded[o] = float(acc);
+      }
+      if ((rc = upload_layer(h, up_name(l), chan(l + 1), chan(l), true, deep_terms, 0, &zero))) return rc;
+      if (l >= 1) rc = upload_layer(h, dec_name(l, 1), 2 * chan(l), chan(l), false, deep_terms, 0, &folded);
+      else rc = upload_layer(h, dec_name(l, 1), 2 * chan(l), chan(l), false, 3, cu / 64, &folded);
+      if (rc) return rc;
+    }
+    if ((rc = upload_layer(h, dec_name(l, 2), chan(l), chan(l), false, terms_at(l)))) return rc;
   }
   if ((rc = expect_dims(h, "outconv.weight", {1, 64, 1, 1}, &w))) return rc;
   if ((rc = expect_dims(h, "outconv.bias", {1}, &b))) return rc;
@@ -1005,6 +1121,8 @@ int wsu_get_info(wsu_handle h, const char* key, int64_t* out) {
   if (!std::strcmp(key, "micro_batch")) *out = h->plan ? h->plan->mb : 0;
   else if (!std::strcmp(key, "last_images")) *out = h->last_nimg;
   else if (!std::strcmp(key, "num_sms")) *out = h->num_sms;
+  else if (!std::strcmp(key, "precision")) *out = h->precision_active;
+  else if (!std::strcmp(key, "bytes_per_image")) *out = h->plan ? int64_t(per_image_bytes(h->nsteps, h->plan->H, h->plan->W, h->precision_active != 0)) : 0;
   else if (!std::strcmp(key, "layers")) *out = h->plan ? int64_t(h->plan->convs.size()) + 1 : 0;
   else return fail(WSU_ERR_INVALID, std::string("unknown info key ") + key);
   return WSU_OK;

@@ -13,6 +13,8 @@
 //      the epilogue of tile i overlaps the MMAs of tile i+1.
 //   Precision: D += Ahi*Whi + Alo*Whi + Ahi*Wlo  (3 bf16 MMAs per algorithmic MAC).
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM owner), warps 2..5 = epilogue.
+#include <type_traits>
+
 #include "conv_mma.h"
 #include "ptx.cuh"
 #include "ws_math.cuh"
@@ -86,8 +88,9 @@ __device__ __forceinline__ void store_pixel8(const Act& o, int b, int oy, int ox
                                              const uint32_t (&l)[4]) {
   const uint4 vh = make_uint4(h[0], h[1], h[2], h[3]), vl = make_uint4(l[0], l[1], l[2], l[3]);
   const size_t off = ((size_t(b) * (o.H + 2) + (oy + 1)) * (o.W + 2) + (ox + 1)) * o.C + c0;
+  const bool two = o.fmt == ACT_SPLIT;   // fp16 maps have one plane (h holds the fp16 words)
   *reinterpret_cast<uint4*>(o.base + off) = vh;
-  *reinterpret_cast<uint4*>(o.base + o.plane + off) = vl;
+  if (two) *reinterpret_cast<uint4*>(o.base + o.plane + off) = vl;
   if (oy == 1 || ox == 1 || oy == o.H - 2 || ox == o.W - 2) {   // reflect-halo duplicates (border pixels only)
     int ys[3], xs[3];
     const int ny = halo_targets(oy, o.H, ys), nx = halo_targets(ox, o.W, xs);
@@ -96,7 +99,7 @@ __device__ __forceinline__ void store_pixel8(const Act& o, int b, int oy, int ox
         if (iy == 0 && ix == 0) continue;   // (oy+1, ox+1) itself was written above
         const size_t d = ((size_t(b) * (o.H + 2) + ys[iy]) * (o.W + 2) + xs[ix]) * o.C + c0;
         *reinterpret_cast<uint4*>(o.base + d) = vh;
-        *reinterpret_cast<uint4*>(o.base + o.plane + d) = vl;
+        if (two) *reinterpret_cast<uint4*>(o.base + o.plane + d) = vl;
       }
   }
 }
@@ -148,8 +151,10 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
                                                       const uint32_t (&h)[16], const uint32_t (&l)[16], const BoxGeo& g,
                                                       const StoreMap& map) {
   const int piece = lane & 3;
+  const int planes = o.fmt == ACT_SPLIT ? 2 : 1;   // fp16 maps: h holds 32 fp16 channels = the same 64-byte row
 #pragma unroll
   for (int plane = 0; plane < 2; ++plane) {
+    if (plane >= planes) break;
     __syncwarp();
     uint4* mine = reinterpret_cast<uint4*>(scratch + lane * kScratchPitch);
     const int wsw = (lane >> 1) & 3;
@@ -227,8 +232,13 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
         for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
       }
       uint32_t h[16], l[16];
+      if (p.out.fmt == ACT_F16) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
+        for (int i = 0; i < 16; ++i) { h[i] = cvt_f16x2(f[2 * i], f[2 * i + 1]); l[i] = 0u; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
+      }
       if (!(p.dbg & 2)) store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap);
       if (p.do_pool && !(p.dbg & 1)) {
         // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16). Each exchange moves
@@ -248,8 +258,13 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
         }
         if (valid) {
           uint32_t h4[4], l4[4];
+          if (p.pool.fmt == ACT_F16) {   // max commutes with the (monotone) rounding: pool(fp16(v)) == fp16(pool(v))
 #pragma unroll
-          for (int i = 0; i < 4; ++i) split_pack2(m8[2 * i], m8[2 * i + 1], h4[i], l4[i]);
+            for (int i = 0; i < 4; ++i) { h4[i] = cvt_f16x2(m8[2 * i], m8[2 * i + 1]); l4[i] = 0u; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_pack2(m8[2 * i], m8[2 * i + 1], h4[i], l4[i]);
+          }
           store_pixel8(p.pool, b, y >> 1, x >> 1, n0 + 16 * int(ox1) + 8 * int(oy1), h4, l4);
         }
       }
@@ -662,10 +677,11 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
             const BoxCoord bn = decode_box(p, s0_n + j);
             tma_prefetch_5d(tm, ch, bn.x0, bn.y0, bn.b, 0);
           }
+          const uint32_t box_bytes = (src0 && p.src0_f16) ? kHaloABytes / 2 : kHaloABytes;   // one fp16 plane or (hi, lo)
           for (int j = 0; j < nsub; ++j) {
             const BoxCoord bc = decode_box(p, s0 + j);
             mbar_wait(&a_empty[as], aph ^ 1);
-            mbar_arrive_expect_tx(&a_full[as], kHaloABytes);
+            mbar_arrive_expect_tx(&a_full[as], box_bytes);
             // padded coords of pixel (y, x) are (y+1, x+1): the box with its halo starts at (y0, x0)
             tma_load_5d(sA + as * kHaloABytes, tm, &a_full[as], ch, bc.x0, bc.y0, bc.b, 0);
             if (++as == C::SA) { as = 0; aph ^= 1; }
@@ -707,44 +723,56 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
             // Taps are issued in groups of three, box-major inside a group: box 0 finishes its last tap three tap-steps
             // (not one) before the item ends, so its ring slot is refilled in time for the next item's second box.
             // (Tap-major order left only ~770 cycles for a 45 KB box load with these short N=64 MMAs.)
-            for (int g = 0; g < 3; ++g) {
-              int wslot[3];
+            // F16 blocks (source 0 of a decoder layer under a reduced precision plan: the up-convolution's output stored as
+            // ONE fp16 plane, weights as an fp16 (hi, lo) pair): one N=128 MMA per K=16 step instead of two.
+            auto issue_block = [&](auto f16_c) {
+              constexpr bool F16 = decltype(f16_c)::value;
+              for (int g = 0; g < 3; ++g) {
+                int wslot[3];
 #pragma unroll
-              for (int j = 0; j < M_SUB; ++j) {
-                if (j < nsub) {
+                for (int j = 0; j < M_SUB; ++j) {
+                  if (j < nsub) {
 #pragma unroll
-                  for (int tt = 0; tt < 3; ++tt) {
-                    const int tap = 3 * g + tt;
-                    if (j == 0) {
-                      wslot[tt] = ws;
-                      mbar_wait(&w_full[ws], wph);
-                      if (++ws == C::SW) { ws = 0; wph ^= 1; }
-                    }
-                    if (tap == 0) {
-                      mbar_wait(&a_full[as], aph);
-                      a_slot[j] = uint32_t(as);
-                      if (++as == C::SA) { as = 0; aph ^= 1; }
-                    }
-                    tc_fence_after();
-                    const uint64_t wd = make_sw128_desc(smem_u32(sW + wslot[tt] * C::W_BYTES));
-                    const uint64_t ad = make_sw128_desc(smem_u32(sA + a_slot[j] * kHaloABytes), kHaloSBO);
-                    const uint32_t tap_off = uint32_t(g * (kHaloTW + 2) + tt) * 128;
-                    const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
+                    for (int tt = 0; tt < 3; ++tt) {
+                      const int tap = 3 * g + tt;
+                      if (j == 0) {
+                        wslot[tt] = ws;
+                        mbar_wait(&w_full[ws], wph);
+                        if (++ws == C::SW) { ws = 0; wph ^= 1; }
+                      }
+                      if (tap == 0) {
+                        mbar_wait(&a_full[as], aph);
+                        a_slot[j] = uint32_t(as);
+                        if (++as == C::SA) { as = 0; aph ^= 1; }
+                      }
+                      tc_fence_after();
+                      const uint64_t wd = make_sw128_desc(smem_u32(sW + wslot[tt] * C::W_BYTES));
+                      const uint64_t ad = make_sw128_desc(smem_u32(sA + a_slot[j] * kHaloABytes), kHaloSBO);
+                      const uint32_t tap_off = uint32_t(g * (kHaloTW + 2) + tt) * 128;
+                      const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      const uint64_t da_hi = desc_at(desc_lo(ad), desc_hi(ad), tap_off + k * 32);
-                      const uint64_t da_lo = desc_at(desc_lo(ad), desc_hi(ad), tap_off + kHaloRows * 128 + k * 32);
-                      const uint64_t dw_hi = desc_at(desc_lo(wd), desc_hi(wd), k * 32);
-                      // B tile of 128 rows = [Whi; Wlo]: columns [0,64) += Ahi*Whi, [64,128) += Ahi*Wlo
-                      umma_bf16(d, da_hi, dw_hi, make_idesc_bf16(128), (c | tap | k) != 0);
-                      umma_bf16(d, da_lo, dw_hi, make_idesc_bf16(64), 1);   // columns [0,64) += Alo*Whi
+                      for (int k = 0; k < 4; ++k) {
+                        const uint64_t da_hi = desc_at(desc_lo(ad), desc_hi(ad), tap_off + k * 32);
+                        const uint64_t dw_hi = desc_at(desc_lo(wd), desc_hi(wd), k * 32);
+                        if constexpr (F16) {
+                          // columns [0,64) += A*Whi, [64,128) += A*Wlo (fp16 operands)
+                          umma_bf16(d, da_hi, dw_hi, make_idesc_f16_m(128, 128), (c | tap | k) != 0);
+                        } else {
+                          const uint64_t da_lo = desc_at(desc_lo(ad), desc_hi(ad), tap_off + kHaloRows * 128 + k * 32);
+                          // B tile of 128 rows = [Whi; Wlo]: columns [0,64) += Ahi*Whi, [64,128) += Ahi*Wlo
+                          umma_bf16(d, da_hi, dw_hi, make_idesc_bf16(128), (c | tap | k) != 0);
+                          umma_bf16(d, da_lo, dw_hi, make_idesc_bf16(64), 1);   // columns [0,64) += Alo*Whi
+                        }
+                      }
+                      if (j == nsub - 1) umma_commit(&w_empty[wslot[tt]]);
+                      if (tap == 8) umma_commit(&a_empty[a_slot[j]]);
                     }
-                    if (j == nsub - 1) umma_commit(&w_empty[wslot[tt]]);
-                    if (tap == 8) umma_commit(&a_empty[a_slot[j]]);
                   }
                 }
               }
-            }
+            };
+            if (p.src0_f16 && c < p.cblocks0) issue_block(std::true_type{});
+            else issue_block(std::false_type{});
           } else {
             for (int tap = 0; tap < 9; ++tap) {
               const int ws_hi = ws;
@@ -867,28 +895,36 @@ cudaError_t launch_halo_t(const ConvParams& p, int num_sms, cudaStream_t stream)
 // the weight ring shrinks. Leader CTA (rank 0) issues all MMAs; activation boxes are loaded by each CTA with the
 // cta_group::2 TMA form that credits the leader's mbarrier; weight half-tiles arrive on a local barrier and the idle
 // MMA warp of the peer CTA relays their completion to the leader.
-template <int N_TILE>
+// TERMS = MMAs per algorithmic MAC. 3: split-bf16 activations (hi, lo planes) x split-bf16 weights, hi*hi + hi*lo + lo*hi.
+// 2 / 1: the input map is ONE fp16 plane (ACT_F16) against fp16 (hi, lo) / fp16 hi-only weights - the layers the precision
+// plan (api.cu, option "precision") runs below three terms. Half-size boxes: the ring holds six of them.
+template <int N_TILE, int TERMS = 3>
 struct H2Cfg {
   static constexpr bool STACKED = (N_TILE == 64);
   static constexpr int M_SUB = 2;                 // box slots per item (x 2 CTAs = 4 boxes share one weight pass)
   static constexpr int ACC_W = 128;
-  static constexpr int SA = 3;
-  static constexpr int W_SLOT = 16384;            // [X tile 8 KB][Y tile 4 KB (stacked) | Z tile 8 KB]
-  static constexpr int W_BYTES = STACKED ? 12288 : 16384;
-  static constexpr int SW = 4;
+  static constexpr int A_BYTES = TERMS == 3 ? kHaloABytes : kHaloABytes / 2;
+  static constexpr int SA = TERMS == 3 ? 3 : (TERMS == 2 ? 4 : 6);   // fp16 boxes are 22.5 KB: an even count keeps the weight ring 1024-byte aligned
+  static constexpr int W_SLOT = TERMS == 1 ? 8192 : 16384;   // [X tile 8 KB][Y tile 4 KB (stacked) | Z tile 8 KB]
+  static constexpr int W_BYTES = STACKED ? 12288 : (TERMS == 1 ? 8192 : 16384);
+  // a tap's weights are consumed in 2 x 4 MMAs: ~1500 / 1000 / 540 cycles with 3 / 2 / 1 terms, against an L2 -> shared
+  // latency of ~2500 cycles per bulk copy: the ring has to be deeper the fewer terms a tap takes
+  static constexpr int SW = TERMS == 3 ? 4 : (TERMS == 2 ? 6 : 8);
+  static_assert((SA * A_BYTES) % 1024 == 0, "pre-swizzled weight tiles need a 1024-byte aligned ring");
   static constexpr int BIAS_BYTES = (N_TILE == 64) ? 256 : 4096;
-  static constexpr int SMEM = SA * kHaloABytes + SW * W_SLOT + kScratchBytes + 1024 + BIAS_BYTES + 256;
+  static constexpr int SMEM = SA * A_BYTES + SW * W_SLOT + kScratchBytes + 1024 + BIAS_BYTES + 512 /*barriers*/;
 };
 
-template <int N_TILE, int EPI, bool COLL = true>
+template <int N_TILE, int EPI, bool COLL = true, int TERMS = 3>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __grid_constant__ ConvParams p) {
-  using C = H2Cfg<N_TILE>;
+  static_assert(TERMS == 3 || N_TILE == 128, "the one- and two-term variants exist for the Cout >= 128 layers only");
+  using C = H2Cfg<N_TILE, TERMS>;
   constexpr int M_SUB = C::M_SUB;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sW = smem + C::SA * kHaloABytes;
+  uint8_t* sW = smem + C::SA * C::A_BYTES;
   uint8_t* sScratch = sW + C::SW * C::W_SLOT;
   float* sBias = reinterpret_cast<float*>(sScratch + kScratchBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + C::BIAS_BYTES);
@@ -910,8 +946,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmapH0);
     prefetch_tmap(&p.tmapH1);
-    for (int i = 0; i < C::SA; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < C::SW; ++i) { mbar_init(&w_full[i], leader ? 2 : 1); mbar_init(&w_empty[i], 1); }
+    prefetch_tmap(&p.tmapW);
+    // a_full / w_full of the LEADER collect the bytes of both CTAs' TMA loads (cta_group::2 loads credit the leader's barrier)
+    // after ONE arrival, the leader's own arrive.expect_tx for twice the per-CTA bytes: the peer issues its loads without
+    // signalling first. (A remote mbarrier.arrive.release.cluster costs a GPU-scope fence, ~900 cycles: paid once per tap by
+    // the weight relay it had made every layer with fewer than three MMAs per MAC wait on the relay, not on the tensor pipe.)
+    for (int i = 0; i < C::SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < C::SW; ++i) { mbar_init(&w_full[i], (C::STACKED && leader) ? 2 : 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
     fence_mbar_init();
   }
@@ -946,9 +987,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
             const BoxCoord bc = decode_box(p, min(s0 + 2 * j + int(rank), p.total_sub - 1));
             mbar_wait(&a_empty[as], aph ^ 1);
             const uint32_t full_leader = mapa_u32(smem_u32(&a_full[as]), 0);
-            if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * kHaloABytes);
-            else mbar_arrive_cluster(full_leader);
-            tma_load_5d_2sm(sA + as * kHaloABytes, tm, full_leader, ch, bc.x0, bc.y0, bc.b, 0);
+            if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * C::A_BYTES);
+            tma_load_5d_2sm(sA + as * C::A_BYTES, tm, full_leader, ch, bc.x0, bc.y0, bc.b, 0);
             if (++as == C::SA) { as = 0; aph ^= 1; }
           }
         }
@@ -969,13 +1009,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
           const uint8_t* lo = hi + plane_bytes;
           uint8_t* dst = sW + ws * C::W_SLOT;
           mbar_wait(&w_empty[ws], wph ^ 1);
-          mbar_arrive_expect_tx(&w_full[ws], C::W_BYTES);
           if constexpr (C::STACKED) {
+            mbar_arrive_expect_tx(&w_full[ws], C::W_BYTES);
             bulk_load(dst, rank == 0 ? hi : lo, 8192, &w_full[ws]);                 // X: rows of [Whi; Wlo] owned by this CTA
             bulk_load(dst + 8192, hi + rank * 4096, 4096, &w_full[ws]);            // Y: this CTA's half of Whi
           } else {
-            bulk_load(dst, hi + rank * 8192, 8192, &w_full[ws]);                    // X: this CTA's 64 rows of Whi
-            bulk_load(dst + 8192, lo + rank * 8192, 8192, &w_full[ws]);             // Z: this CTA's 64 rows of Wlo
+            // the packed weights seen as rows of 128 B: 64-row boxes, raw copy (they are stored pre-swizzled)
+            const uint32_t full_leader = mapa_u32(smem_u32(&w_full[ws]), 0);
+            const int row_hi = (nt * chunks + q) * 2 * N_TILE + int(rank) * 64;
+            if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * C::W_BYTES);
+            tma_load_2d_2sm(dst, &p.tmapW, full_leader, 0, row_hi);                                      // X: this CTA's 64 rows of Whi
+            if constexpr (TERMS != 1) tma_load_2d_2sm(dst + 8192, &p.tmapW, full_leader, 0, row_hi + N_TILE);   // Z: ... of Wlo
           }
           if (++ws == C::SW) { ws = 0; wph ^= 1; }
         }
@@ -984,19 +1028,21 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
   } else if (warp == 1) {
     if (elect_one()) {
       if (!leader) {
-        // ===================================================== peer: relay weight arrivals to the leader's barrier
-        int ws = 0;
-        uint32_t wph = 0;
-        for (int item = pair; item < items; item += npairs) {
-          for (int q = 0; q < p.cblocks * 9; ++q) {
-            mbar_wait(&w_full[ws], wph);
-            mbar_arrive_cluster(mapa_u32(smem_u32(&w_full[ws]), 0));
-            if (++ws == C::SW) { ws = 0; wph ^= 1; }
+        // ===================================================== peer (stacked Cout = 64 variant only): relay weight arrivals
+        if constexpr (C::STACKED) {
+          int ws = 0;
+          uint32_t wph = 0;
+          for (int item = pair; item < items; item += npairs) {
+            for (int q = 0; q < p.cblocks * 9; ++q) {
+              mbar_wait(&w_full[ws], wph);
+              mbar_arrive_cluster(mapa_u32(smem_u32(&w_full[ws]), 0));
+              if (++ws == C::SW) { ws = 0; wph ^= 1; }
+            }
           }
         }
       } else {
         // ===================================================== leader: MMA issuer for the pair
-        constexpr uint32_t idesc = make_idesc_bf16_m(256, N_TILE);
+        constexpr uint32_t idesc = TERMS == 3 ? make_idesc_bf16_m(256, N_TILE) : make_idesc_f16_m(256, N_TILE);
         int as = 0, ws = 0, acs = 0;
         uint32_t aph = 0, wph = 0, acph = 0;
         for (int item = pair; item < items; item += npairs) {
@@ -1021,7 +1067,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
                     if (++as == C::SA) { as = 0; aph ^= 1; }
                   }
                   tc_fence_after();
-                  const uint64_t ad = make_sw128_desc(smem_u32(sA + a_slot[j] * kHaloABytes), kHaloSBO);
+                  const uint64_t ad = make_sw128_desc(smem_u32(sA + a_slot[j] * C::A_BYTES), kHaloSBO);
                   const uint64_t wxd = make_sw128_desc(w_x), wyd = make_sw128_desc(w_y);
                   const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
 #pragma unroll
@@ -1030,7 +1076,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
                     const uint64_t da_lo = desc_at(desc_lo(ad), desc_hi(ad), tap_off + kHaloRows * 128 + k * 32);
                     const uint64_t dw_x = desc_at(desc_lo(wxd), desc_hi(wxd), k * 32);
                     const uint64_t dw_y = desc_at(desc_lo(wyd), desc_hi(wyd), k * 32);
-                    if constexpr (C::STACKED) {
+                    if constexpr (TERMS == 2) {          // fp16 A x (Whi, Wlo): A read from shared memory once
+                      umma_bf16_2sm_a_fill(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
+                      umma_bf16_2sm_a_lastuse(d, da_hi, dw_y, idesc, 1);
+                    } else if constexpr (TERMS == 1) {   // fp16 A x fp16 W
+                      umma_bf16_2sm(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
+                    } else if constexpr (C::STACKED) {
                       umma_bf16_2sm(d, da_hi, dw_x, make_idesc_bf16_m(256, 128), (c | tap | k) != 0);  // Ahi * [Whi; Wlo]
                       umma_bf16_2sm(d, da_lo, dw_y, make_idesc_bf16_m(256, 64), 1);                    // Alo * Whi
                     } else {
@@ -1121,7 +1172,7 @@ cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kHaloThreads);
-  cfg.dynamicSmemBytes = H2Cfg<N_TILE>::SMEM;
+  cfg.dynamicSmemBytes = (N_TILE == 128 && p.terms == 2) ? H2Cfg<128, 2>::SMEM : (N_TILE == 128 && p.terms == 1) ? H2Cfg<128, 1>::SMEM : H2Cfg<N_TILE>::SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1130,6 +1181,11 @@ cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if constexpr (N_TILE == 128 && EPI == EPI_ACT) {
+    if (p.terms == 2) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 2>, p);
+    if (p.terms == 1) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 1>, p);
+  }
+  if (p.terms != 3) return cudaErrorInvalidValue;
   if (N_TILE == 128 && !p.a_collector) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<N_TILE, EPI, false>, p);
   return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<N_TILE, EPI, true>, p);
 }
@@ -1139,11 +1195,13 @@ cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream
 // The four phases are stacked along N and the whole (hi, lo) weight set of the CTA's N tile (128 KB) stays in shared
 // memory, so each activation box is read exactly once per N tile and the kernel is bound by its output writes.
 constexpr int kUpThreads = 320;
-constexpr int kUpSA = 2;
 
-template <int N_TILE>
+// TERMS as in the CTA-pair convolution: 3 = split-bf16 input (hi, lo planes), 2 / 1 = ONE fp16 input plane against fp16
+// (hi, lo) / hi-only weights. The output format (p.out.fmt) is independent of it.
+template <int N_TILE, int TERMS = 3>
 __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_constant__ UpconvParams p) {
-  constexpr int kBoxBytes = kABytes;  // 32 KB: hi + lo tile of 128 pixels x 64 channels
+  constexpr int kBoxBytes = TERMS == 3 ? kABytes : kABytes / 2;  // hi + lo tile (32 KB) or one fp16 tile of 128 pixels x 64 channels
+  constexpr int kUpSA = TERMS == 3 ? 2 : 4;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;                       // cblocks x (hi | lo) x N_TILE rows x 128 B  (<= 128 KB)
@@ -1184,8 +1242,11 @@ __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_
       // weights of this N tile: resident for the whole kernel
       const uint32_t wbytes = uint32_t(p.cblocks) * 2 * w_tile_bytes;
       const uint8_t* wsrc = p.wres + size_t(nt) * wbytes;
-      mbar_arrive_expect_tx(w_bar, wbytes);
-      for (int i = 0; i < p.cblocks * 2; ++i) bulk_load(sW + i * w_tile_bytes, wsrc + size_t(i) * w_tile_bytes, w_tile_bytes, w_bar);
+      mbar_arrive_expect_tx(w_bar, TERMS == 1 ? wbytes / 2 : wbytes);
+      for (int i = 0; i < p.cblocks * 2; ++i) {
+        if (TERMS == 1 && (i & 1)) continue;   // hi tiles only
+        bulk_load(sW + i * w_tile_bytes, wsrc + size_t(i) * w_tile_bytes, w_tile_bytes, w_bar);
+      }
       int as = 0;
       uint32_t aph = 0;
       for (int box = first_box; box < p.total_boxes; box += box_step) {
@@ -1201,7 +1262,7 @@ __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_bf16(N_TILE);
+      constexpr uint32_t idesc = TERMS == 3 ? make_idesc_bf16(N_TILE) : make_idesc_f16_m(128, N_TILE);
       int as = 0, acs = 0;
       uint32_t aph = 0, acph = 0;
       mbar_wait(w_bar, 0);
@@ -1219,8 +1280,8 @@ __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_
             const uint64_t da_hi = make_sw128_desc(a_hi + k * 32), da_lo = make_sw128_desc(a_lo + k * 32);
             const uint64_t dw_hi = make_sw128_desc(w_hi + k * 32), dw_lo = make_sw128_desc(w_lo + k * 32);
             umma_bf16(d, da_hi, dw_hi, idesc, (c | k) != 0);
-            umma_bf16(d, da_lo, dw_hi, idesc, 1);
-            umma_bf16(d, da_hi, dw_lo, idesc, 1);
+            if constexpr (TERMS == 3) umma_bf16(d, da_lo, dw_hi, idesc, 1);
+            if constexpr (TERMS >= 2) umma_bf16(d, da_hi, dw_lo, idesc, 1);
           }
           umma_commit(&a_empty[as]);
           if (++as == kUpSA) { as = 0; aph ^= 1; }
@@ -1252,11 +1313,21 @@ __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_
         const int col0 = cc * 32;
         const int pos = col0 / p.co_t, cl = col0 % p.co_t;
         uint32_t h[16], l[16];
+        if (p.out.fmt == ACT_F16) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bq = *reinterpret_cast<const float4*>(sBias + cl + 4 * i);
-          split_pack2(__uint_as_float(v[4 * i]) + bq.x, __uint_as_float(v[4 * i + 1]) + bq.y, h[2 * i], l[2 * i]);
-          split_pack2(__uint_as_float(v[4 * i + 2]) + bq.z, __uint_as_float(v[4 * i + 3]) + bq.w, h[2 * i + 1], l[2 * i + 1]);
+          for (int i = 0; i < 8; ++i) {
+            const float4 bq = *reinterpret_cast<const float4*>(sBias + cl + 4 * i);
+            h[2 * i] = cvt_f16x2(__uint_as_float(v[4 * i]) + bq.x, __uint_as_float(v[4 * i + 1]) + bq.y);
+            h[2 * i + 1] = cvt_f16x2(__uint_as_float(v[4 * i + 2]) + bq.z, __uint_as_float(v[4 * i + 3]) + bq.w);
+            l[2 * i] = l[2 * i + 1] = 0u;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bq = *reinterpret_cast<const float4*>(sBias + cl + 4 * i);
+            split_pack2(__uint_as_float(v[4 * i]) + bq.x, __uint_as_float(v[4 * i + 1]) + bq.y, h[2 * i], l[2 * i]);
+            split_pack2(__uint_as_float(v[4 * i + 2]) + bq.z, __uint_as_float(v[4 * i + 3]) + bq.w, h[2 * i + 1], l[2 * i + 1]);
+          }
         }
         const BoxGeo geo{b, ty * 8, tx * 16, 4, p.H, p.W, 1, pos};
         const StoreMap smap = make_store_map(p.out, geo, lane, quad * 32);   // per chunk: the output phase changes with it
@@ -1276,7 +1347,7 @@ __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_
     tmem_dealloc(tmem_base, 512);
   }
 }
-constexpr int kUpSmem = kUpconvResBytes + kUpSA * kABytes + kScratchBytes + 1024 + 256 + 256;
+constexpr int kUpSmem = kUpconvResBytes + 2 * kABytes + kScratchBytes + 1024 + 256 + 256;
 
 }  // namespace
 
@@ -1302,11 +1373,23 @@ cudaError_t conv_mma_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128>::SMEM);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128, 2>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128, 1>::SMEM);
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upconv_res_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upconv_res_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upconv_res_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upconv_res_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upconv_res_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(upconv_res_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
   return e;
 }
 
@@ -1344,9 +1427,17 @@ cudaError_t launch_upconv_res(const UpconvParams& p, int n_tile, int num_sms, cu
   const int max_useful = p.total_boxes * p.n_tiles;
   if (grid > max_useful) grid = max_useful;
   if (grid <= 0) return cudaErrorInvalidValue;
-  if (n_tile == 256) upconv_res_kernel<256><<<grid, kUpThreads, kUpSmem, stream>>>(p);
-  else if (n_tile == 128) upconv_res_kernel<128><<<grid, kUpThreads, kUpSmem, stream>>>(p);
-  else return cudaErrorInvalidValue;
+  if (n_tile != 256 && n_tile != 128) return cudaErrorInvalidValue;
+  if (p.terms == 3) {
+    if (n_tile == 256) upconv_res_kernel<256><<<grid, kUpThreads, kUpSmem, stream>>>(p);
+    else upconv_res_kernel<128><<<grid, kUpThreads, kUpSmem, stream>>>(p);
+  } else if (p.terms == 2) {
+    if (n_tile == 256) upconv_res_kernel<256, 2><<<grid, kUpThreads, kUpSmem, stream>>>(p);
+    else upconv_res_kernel<128, 2><<<grid, kUpThreads, kUpSmem, stream>>>(p);
+  } else if (p.terms == 1) {
+    if (n_tile == 256) upconv_res_kernel<256, 1><<<grid, kUpThreads, kUpSmem, stream>>>(p);
+    else upconv_res_kernel<128, 1><<<grid, kUpThreads, kUpSmem, stream>>>(p);
+  } else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 }  // namespace wsu

@@ -15,6 +15,7 @@ struct alignas(64) ConvParams {
   CUtensorMap tmapA1;  // second concat source (skip); unused when cblocks == cblocks0
   CUtensorMap tmapH0;  // same sources with the haloed box (64 ch, 10, 18, 1 img, 2 planes) of the halo kernel
   CUtensorMap tmapH1;
+  CUtensorMap tmapW;   // packed weights as rows of 128 B, box = 64 rows (CTA-pair kernels: each CTA loads its half of a tile)
   const uint8_t* wpack;  // packed + pre-swizzled split-bf16 weights, see pack_conv_weights()
   const float* bias;     // [Cout]
   int cblocks0;          // 64-channel blocks taken from source 0
@@ -41,6 +42,9 @@ struct alignas(64) ConvParams {
   int l2_prefetch;       // halo kernels: warm L2 with the boxes of the CTA's next work item
   int dbg;               // timing experiments only (env WSU_DBG): bit 0 skips the pooled output, bit 1 the main output stores
   int a_collector;       // Cout >= 128 layers: A_hi stays in the tensor core's A collector for its second product
+  int terms;             // MMAs per MAC: 3 (split-bf16 inputs) or 2 / 1 (ONE fp16 input plane; CTA-pair kernel, Cout >= 128)
+  int src0_f16;          // Cout = 64 halo kernel: the channel blocks of source 0 are ONE fp16 plane against fp16 (hi, lo) weights
+                         // (two terms, one stacked N=128 MMA per K step); source 1 stays three-term split-bf16
   // EPI_ACT
   int relu;
   int upsample;          // 1: write phase (pos>>1, pos&1) of a 2x upsampled map (ConvTranspose2d k=2,s=2)
@@ -73,6 +77,7 @@ struct alignas(64) UpconvParams {
   const uint8_t* wres;    // [n_tiles][cblocks][hi tile | lo tile], rows r -> (phase r / co_t, channel nt*co_t + r % co_t)
   const float* bias;      // [Cout]
   int cblocks, n_tiles, co_t;
+  int terms;              // MMAs per MAC: 3 (split-bf16 input) or 2 / 1 (one fp16 input plane)
   int B, H, W;            // input dims
   int tiles_x, tiles_y, total_boxes;
   Act out;                // (2H, 2W) destination

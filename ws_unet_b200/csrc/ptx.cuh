@@ -199,6 +199,14 @@ __device__ __forceinline__ void tma_load_5d_2sm(void* dst, const CUtensorMap* m,
       "r"(c3), "r"(c4)
       : "memory");
 }
+// 2-D tiled load, same crediting rule (used for the packed weight rows of the CTA-pair kernels)
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot_in_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)),
                "r"(ncols)
@@ -244,6 +252,11 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
 }
 __host__ __device__ constexpr uint32_t make_idesc_bf16_m(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+// same with fp16 A/B operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16_m(int m, int n) {
+  return (1u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }

@@ -10,6 +10,7 @@
 //   * finalize_kernel     - deterministic fixed-order reduction of the partial sums to beta_hat / l1 per image.
 //   * pack / unpack       - NCHW fp32 <-> split-bf16 NHWC, used by the per-layer parity tests.
 #include <algorithm>
+#include <cuda_fp16.h>
 #include "stencil.h"
 #include "ws_math.cuh"
 
@@ -965,7 +966,8 @@ __global__ void unpack_kernel(Act src, float* __restrict__ dst, int with_halo) {
     const int b = int(i / (size_t(Wo) * Ho * src.C));
     const int sy = with_halo ? y : y + 1, sx = with_halo ? x : x + 1;
     const size_t off = ((size_t(b) * (src.H + 2) + sy) * (src.W + 2) + sx) * src.C + c;
-    dst[i] = __bfloat162float(src.base[off]) + __bfloat162float(src.base[src.plane + off]);
+    if (src.fmt == ACT_F16) dst[i] = __half2float(reinterpret_cast<const __half*>(src.base)[off]);
+    else dst[i] = __bfloat162float(src.base[off]) + __bfloat162float(src.base[src.plane + off]);
   }
 }
 

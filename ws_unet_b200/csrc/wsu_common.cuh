@@ -13,10 +13,16 @@
 
 namespace wsu {
 
+// Storage formats of a feature map. ACT_SPLIT: two bf16 planes (hi, lo) = 16 significand bits, read by the three-term
+// layers. ACT_F16: ONE fp16 plane (11 significand bits), read by the layers the precision plan runs with one or two MMAs per
+// MAC (api.cu: "precision" option) - half the HBM bytes and half the TMA box.
+enum : int { ACT_SPLIT = 0, ACT_F16 = 1 };
+
 struct Act {
-  __nv_bfloat16* base;  // plane 0 (hi); plane 1 (lo) starts at base + plane
+  __nv_bfloat16* base;  // plane 0 (hi, or the fp16 plane); plane 1 (lo) starts at base + plane
   size_t plane;         // elements per plane = B*(H+2)*(W+2)*C
   int B, H, W, C;
+  int fmt = ACT_SPLIT;
 };
 
 __host__ __device__ inline size_t act_plane_elems(int B, int H, int W, int C) {
@@ -39,6 +45,13 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi2, uin
   const float ah = __uint_as_float(hi2 << 16);
   const float bh = __uint_as_float(hi2 & 0xffff0000u);
   lo2 = cvt_bf16x2(a - ah, b - bh);  // a - ah is exact in fp32 (Sterbenz-like: ah is a rounded to 8 bits)
+}
+
+// two floats -> one fp16x2 word (element 0 in the low half), round to nearest even
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
 }
 
 // Packed fp32 pair arithmetic (Blackwell FFMA2): acc.{lo,hi} = fma.rn(v, w.{lo,hi}, acc.{lo,hi}) - two independent IEEE

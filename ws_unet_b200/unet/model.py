@@ -17,6 +17,9 @@ from torch import nn
 from .. import _native
 
 
+PRECISIONS = {'bf16x3': 0, 'fp16x2': 1, 'fp16x1': 2}   # wsu_set_option(h, "precision", .)
+
+
 class UniformDropout(nn.Module):
     """Input dropout of the reference (unet.py:15-51): every pixel is kept with probability 1-drop_rate and otherwise
     replaced by its KB prediction (reflect padding). With drop_rate=0 (every shipped inference path,
@@ -95,6 +98,7 @@ class UNet(nn.Module):
         self._handle = None       # wsu_handle (ctypes.c_void_p)
         self._handle_device = None
         self._weights_key = None
+        self._precision = 'bf16x3'
 
     # ------------------------------------------------------------------ native handle management
     def __getstate__(self):  # joblib workers pickle the model (src/ws/estimate.py:139-146)
@@ -102,7 +106,7 @@ class UNet(nn.Module):
         state['_handle'] = None
         state['_handle_device'] = None
         state['_weights_key'] = None
-        return state
+        return state   # _precision travels with the pickle
 
     def __del__(self):
         try:
@@ -129,6 +133,7 @@ class UNet(nn.Module):
             _native.check(lib.wsu_create(ctypes.byref(h), dev_index, self.nsteps, self.in_channels, self.out_channels),
                           'wsu_create')
             self._handle, self._handle_device, self._weights_key = h, dev_index, None
+            _native.check(lib.wsu_set_option(h, b'precision', PRECISIONS[getattr(self, '_precision', 'bf16x3')]), 'precision')
         key = self._key()
         if key != self._weights_key:
             for name, t in self.state_dict().items():
@@ -183,6 +188,48 @@ class UNet(nn.Module):
         """Force a re-pack of the device weights on the next forward. Needed only after edits through `.data`
         (which do not bump tensor version counters); load_state_dict, optimizer steps and .to() are detected."""
         self._weights_key = None
+
+    # ------------------------------------------------------------------ precision plan (no counterpart in the reference)
+    def set_precision(self, mode: str, device=None):
+        """Arithmetic of the layers whose input lives at UNet level >= 1 (e21.., d3x, up-convolutions):
+        'bf16x3' (default) - split-bf16 operands, three MMAs per MAC, like the full-resolution layers e12 / d41 / d42;
+        'fp16x2' / 'fp16x1' - ONE fp16 activation plane against fp16 (hi, lo) / fp16 weights, two / one MMA per MAC and
+        half the activation bytes. Whether a reduced plan keeps the prediction inside the 1e-3 px bar depends on how much
+        of the output the deep path carries for the weights at hand - use `calibrate_precision` to decide."""
+        if mode not in PRECISIONS:
+            raise ValueError(f'precision must be one of {list(PRECISIONS)}')
+        self._precision = mode
+        if self._handle is not None:
+            _native.check(_native.load().wsu_set_option(self._handle, b'precision', PRECISIONS[mode]), 'precision')
+        return self
+
+    def active_precision(self, device=None) -> str:
+        """The plan the library actually runs (reduced plans need shared-memory-resident up-convolutions: unet_1, unet_2)."""
+        dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        out = ctypes.c_int64()
+        _native.check(_native.load().wsu_get_info(self.native_handle(dev), b'precision', ctypes.byref(out)))
+        return {v: k for k, v in PRECISIONS.items()}[int(out.value)]
+
+    @torch.no_grad()
+    def calibrate_precision(self, images: torch.Tensor, budget_px: float = 2e-4, modes=('fp16x1', 'fp16x2')) -> dict:
+        """Pick the cheapest precision plan whose predictions on `images` ((B,C,H,W) uint8 pixels or float32 in [0,1], on the
+        device) stay within `budget_px` (max-abs, pixel units) of the three-term plan, which itself sits 2-5e-5 px from the
+        FP32 reference. Leaves the chosen plan active and returns {'chosen', 'max_abs_px': {mode: err}, 'budget_px'}."""
+        self.set_precision('bf16x3')
+        ref = self(images)
+        report = {'chosen': 'bf16x3', 'max_abs_px': {}, 'budget_px': budget_px, 'images': int(images.shape[0])}
+        for mode in modes:
+            self.set_precision(mode)
+            if self.active_precision(images.device) != mode:
+                report['max_abs_px'][mode] = None      # not available for this depth
+                continue
+            err = ((self(images) - ref).abs().max() * 255.).item()
+            report['max_abs_px'][mode] = err
+            if err == err and err <= budget_px:
+                report['chosen'] = mode
+                return report
+        self.set_precision('bf16x3')
+        return report
 
     def set_micro_batch(self, n: int, device=None):
         """Images per pass through the layer chain (0 = auto from free HBM budget)."""

@@ -357,7 +357,7 @@ def run_ours(args):
     host_out = torch.empty(2, per_gpu, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        _native.check(lib.wsu_unet_ws_estimate_host(h, ctypes.c_void_p(host_img.data_ptr()), per_gpu, S, S, 0, 1, 1,
+        _native.check(lib.wsu_unet_ws_estimate_host(h, ctypes.c_void_p(host_img.data_ptr()), per_gpu, S, S, 0, 1, 1, 0,
                                                     ctypes.c_void_p(host_out[0].data_ptr()), ctypes.c_void_p(host_out[1].data_ptr())))
 
     e2e_steps = args.steps if not args.images else 1

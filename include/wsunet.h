@@ -58,7 +58,10 @@ int wsu_commit_weights(wsu_handle h);
  *          "l2_prefetch" (default 0; 1: 3x3 kernels warm L2 with the boxes of their next work item - measured 1 % slower);
  *          "a_collector" (default 1: the CTA-pair kernel issues hi*hi, hi*lo, lo*hi and keeps A_hi in the tensor core's
  *                         A collector for its second product; 0: every MMA re-reads A from shared memory);
- *          "cta_pair" (default 1: 3x3 layers with Cout >= 128 run as CTA pairs, tcgen05 cta_group::2; 0 never; 2 all);
+ *          "cta_pair" (default 2: every 3x3 layer runs as CTA pairs, tcgen05 cta_group::2; 1: Cout >= 128 layers only; 0 never);
+ *          "precision" (default 0: every layer three-term split-bf16; 1 / 2: the layers whose input lives at UNet level >= 1
+ *                       read ONE fp16 activation plane with two / one MMA per MAC - see ws_unet_b200/unet/model.py
+ *                       set_precision / calibrate_precision; wsu_get_info "precision" reports what is active);
  *          "upconv_resident" (default 1: transposed convs keep their weights in shared memory; 0: per-phase kernel);
  *          "halo" (default 1: 3x3 layers load one haloed box per channel block; 0: per-tap reload kernel);
  *          "profile" (1: record CUDA events around every layer launch of the last micro-batch) */
@@ -73,14 +76,17 @@ int wsu_unet_forward(wsu_handle h, const void* x_dev, int x_dtype, float* y_dev,
  *   crop=1, weighted=0, clip=0 : src/unet/evaluate.py:109-139 predict_unet   (beta_hat, l1)
  *   crop=1, weighted in {0,1,-1}, clip=1 : src/ws/estimate.py:55-136 attack with the UNet pixel_estimator
  *   crop=0, weighted=0, clip=1 : src/_defs/losses.py:46-61 WSLoss._error betas_hat (float images allowed)
+ *   correct_bias=1 (uint8 images): estimate.py:126-128 - a second pass of the predictor over the LSB-difference image
+ *     (x_bar - x) / 255, formed inside the first-layer kernel, whose head accumulates sum w (x - x_bar) x_bias next to the
+ *     first pass's sums; beta_hat -= beta_hat * that. No prediction map leaves the GPU's on-chip memory in either pass.
  * img_dev (B,1,H,W) uint8 or float32 in [0,1]; beta_dev (B) float32; l1_dev (B) or NULL; yhat_dev (B,1,H,W) or NULL. */
 int wsu_unet_ws_estimate(wsu_handle h, const void* img_dev, int img_dtype, int B, int H, int W, int weighted, int clip,
-                         int crop, float* beta_dev, float* l1_dev, float* yhat_dev, void* stream);
+                         int crop, int correct_bias, float* beta_dev, float* l1_dev, float* yhat_dev, void* stream);
 
 /* Same, but img_host/beta_host/l1_host are HOST buffers: chunks are copied H2D on a side stream overlapping compute,
  * results copied back; returns after everything has completed. This is the end-to-end call bench.py times. */
 int wsu_unet_ws_estimate_host(wsu_handle h, const uint8_t* img_host, int B, int H, int W, int weighted, int clip, int crop,
-                              float* beta_host, float* l1_host);
+                              int correct_bias, float* beta_host, float* l1_host);
 
 /* ---- linear predictors, no handle needed: src/filters/evaluate.py:136-146 infere_single/get_filter_estimator.
  * xhat_dev (B,H-2,W-2) float32 in pixel units ('valid' 3x3 correlation). */
@@ -114,7 +120,7 @@ int wsu_ws_grad_prediction(int device, const void* img_dev, int img_dtype, const
 int wsu_debug_layer(wsu_handle h, const char* name, float* dst_dev, size_t dst_capacity_elems, int with_halo,
                     int64_t* dims_out, void* stream);
 /* introspection: "micro_batch" (images per pass of the current plan), "last_images" (images in the last pass that ran),
- * "num_sms", "layers" (kernel launches per pass) */
+ * "num_sms", "layers" (kernel launches per pass), "precision" (active plan), "bytes_per_image" (feature-map bytes per image) */
 int wsu_get_info(wsu_handle h, const char* key, int64_t* out);
 /* per-layer device times (ms) of the last micro-batch when option "profile" is on; returns the layer count (>= 0)
  * or a negative status. wsu_profile_name(i) names entry i ("e11", "e12", ..., "d42"). */

@@ -30,8 +30,8 @@ PROTOTYPES = {
     "wsu_commit_weights": (_i, [_vp]),
     "wsu_set_option": (_i, [_vp, _c.c_char_p, _i64]),
     "wsu_unet_forward": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp]),
-    "wsu_unet_ws_estimate": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "wsu_unet_ws_estimate_host": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "wsu_unet_ws_estimate": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "wsu_unet_ws_estimate_host": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "wsu_filter_predict": (_i, [_i, _vp, _i, _i, _vp, _i, _i, _i, _vp]),
     "wsu_filter_ws_estimate": (_i, [_i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "wsu_filter_ws_estimate_host": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i]),

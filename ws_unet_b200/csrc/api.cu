@@ -125,12 +125,12 @@ int make_act_tmap(CUtensorMap* m, const Act& a, int TW, int TH) {
 
 // 2-D map over a layer's packed weights seen as rows of 128 B (64 two-byte elements): box = 64 rows = one CTA's half of a
 // 128-row tile. No swizzle: the tiles are stored in the order the tensor core reads them.
-int make_w_tmap(CUtensorMap* m, const void* wpack, size_t bytes) {
+int make_w_tmap(CUtensorMap* m, const void* wpack, size_t bytes, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(WSU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {64, cuuint64_t(bytes / 128)};
   cuuint64_t strides[1] = {128};
-  cuuint32_t box[2] = {64, 64};
+  cuuint32_t box[2] = {64, cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wpack), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -205,7 +205,8 @@ struct wsu_context {
   // three CUDA-core producer warps cannot keep up with the tensor pipe (e12 2.66 ms vs 0.56 + 1.83 ms per 32 images), so it
   // is off by default.
   bool fuse_e11 = false;
-  int use_pair = 1;  // 3x3 layers as CTA pairs (tcgen05 cta_group::2): 0 never, 1 Cout>=128 layers (measured win), 2 all
+  int use_pair = 2;  // 3x3 layers as CTA pairs (tcgen05 cta_group::2): 0 never, 1 Cout>=128 layers only, 2 all (default: with the weight
+                     // tiles loaded by cta_group::2 TMA the Cout=64 layers gain 3-6 % too; they lost before, behind the per-tap relay fence)
   int dbg = 0;            // env WSU_DBG: knock-out switches for timing experiments (results are wrong when set)
   int a_collector = 1;    // option "a_collector" (default on, +0.4 % measured): Cout >= 128 layers reuse A_hi from the A collector (hi*hi, hi*lo, lo*hi order)
   int l2_prefetch = 0;    // halo kernels prefetch the next item's boxes into L2 (option "l2_prefetch"); measured 1 % slower
@@ -284,7 +285,8 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   rc = make_act_tmap(&p.tmapH1, src1 ? *src1 : src0, kHaloTW + 2, kHaloTH + 2);
   if (rc) return rc;
   p.wpack = lw.wpack;
-  if ((rc = make_w_tmap(&p.tmapW, lw.wpack, lw.wpack_bytes))) return rc;
+  if ((rc = make_w_tmap(&p.tmapW, lw.wpack, lw.wpack_bytes, 64))) return rc;
+  if ((rc = make_w_tmap(&p.tmapW32, lw.wpack, lw.wpack_bytes, 32))) return rc;
   p.bias = lw.bias;
   p.cblocks0 = src0.C / 64;
   p.cblocks = lw.cin / 64;
@@ -454,8 +456,10 @@ int pick_micro_batch(wsu_context* h, int B, int H, int W) {
 }
 
 // one micro-batch through the layer chain. img points at this micro-batch's first image.
+// bias_pass: the predictor runs on the LSB-difference image (x_bar - x) / 255 of `img` and the head adds sum w (x - x_bar) x_bias
+// to the partial records of the preceding normal pass (src/ws/estimate.py:126-128)
 int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const void* ws_img, int ws_dtype, float* yhat,
-              int weighted, int crop, cudaStream_t st) {
+              int weighted, int crop, cudaStream_t st, bool bias_pass = false) {
   Plan& pl = *h->plan;
   h->last_nimg = nimg;
   Act first = pl.acts.at(enc_name(0, 1));
@@ -479,11 +483,11 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
   if (!pl.convs.empty()) {
     const ConvParams& c0 = pl.convs[0].first;
     const int nt0 = pl.convs[0].second.first, epi0 = pl.convs[0].second.second;
-    fuse_first = h->fuse_e11 && h->use_halo && h->use_pair != 2 && h->in_ch == 1 && epi0 == EPI_ACT && nt0 == 64 &&
-                 c0.cblocks == 1 && c0.ntaps == 9;
+    fuse_first = h->fuse_e11 && h->use_halo && h->in_ch == 1 && epi0 == EPI_ACT && nt0 == 64 &&
+                 c0.cblocks == 1 && c0.ntaps == 9 && !bias_pass;
   }
   if (!fuse_first)
-    LAUNCH_TRY(launch_first_conv(img, img_dtype == WSU_F32, h->in_ch, h->e11_w, h->e11_b,
+    LAUNCH_TRY(launch_first_conv(img, bias_pass ? 2 : (img_dtype == WSU_F32 ? 1 : 0), h->in_ch, h->e11_w, h->e11_b,
                                  Act{first.base, first.plane, nimg, first.H, first.W, first.C}, st));
   for (size_t i = 0; i < pl.convs.size(); ++i) {
     ConvParams p = pl.convs[i].first;
@@ -511,10 +515,18 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
       p.partials = ws_img ? pl.partials : nullptr;
       p.weighted = weighted;
       p.crop = crop;
+      p.bias_pass = bias_pass ? 1 : 0;
     }
     mark(i + 1);
-    if (p.src0_f16) {
-      LAUNCH_TRY(launch_conv_halo(p, n_tile, epi, h->num_sms, st));
+    if (i == 0 && fuse_first) {
+      LAUNCH_TRY(launch_conv_halo(p, n_tile, epi, h->num_sms, st));   // e11 computed by e12's producer warps (single-CTA kernel)
+    } else if (p.src0_f16) {
+      if (h->use_pair == 2) {
+        p.total_items = ((p.total_sub + 3) / 4) * p.n_tiles;
+        LAUNCH_TRY(launch_conv_halo2(p, n_tile, epi, h->num_sms, st));
+      } else {
+        LAUNCH_TRY(launch_conv_halo(p, n_tile, epi, h->num_sms, st));
+      }
     } else if (pl.up_idx[i] >= 0 && (h->use_upres || p.terms != 3)) {
       UpconvParams u = pl.ups[pl.up_idx[i]];
       if (nimg != pl.mb) { u.B = nimg; u.total_boxes = nimg * u.tiles_x * u.tiles_y; }
@@ -532,7 +544,7 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
 }
 
 int unet_ws_device(wsu_context* h, const void* img, int dtype, int B, int H, int W, bool want_ws, int weighted, int clip,
-                   int crop, float* beta, float* l1, float* yhat, cudaStream_t st) {
+                   int crop, int correct_bias, float* beta, float* l1, float* yhat, cudaStream_t st) {
   if (!h) return fail(WSU_ERR_INVALID, "null handle");
   if (!h->committed) return fail(WSU_ERR_STATE, "weights not committed (call wsu_commit_weights)");
   int rc = check_shape(h, B, H, W);
@@ -544,6 +556,8 @@ int unet_ws_device(wsu_context* h, const void* img, int dtype, int B, int H, int
     if (weighted != 0 && !crop)
       return fail(WSU_ERR_INVALID, "local-variance weights exist only on the interior (crop=1), estimate.py:94-96");
     if (crop && (H < 3 || W < 3)) return fail(WSU_ERR_INVALID, "crop=1 needs H, W >= 3");
+    if (correct_bias && dtype != WSU_U8)
+      return fail(WSU_ERR_INVALID, "correct_bias needs uint8 images (the second pass runs on the integer difference x_bar - x, estimate.py:127)");
   }
   DEVICE_SCOPE(h->device);
   if (!h->ev_chain) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_chain, cudaEventDisableTiming));
@@ -565,11 +579,14 @@ int unet_ws_device(wsu_context* h, const void* img, int dtype, int B, int H, int
     if ((rc = run_chain(h, im, dtype, nimg, want_ws ? im : nullptr, dtype, yhat ? yhat + size_t(b0) * px : nullptr, weighted, crop,
                         st)))
       return rc;
+    if (want_ws && correct_bias) {   // second predictor pass on the difference image; only slot 3 of the partial records changes
+      if ((rc = run_chain(h, im, dtype, nimg, im, dtype, nullptr, weighted, crop, st, true))) return rc;
+    }
     if (want_ws) {
       const float npix = crop ? float(H - 2) * float(W - 2) : float(H) * float(W);
       const ConvParams& hp = h->plan->convs.back().first;
       const int records = h->use_halo ? hp.sub_x * hp.sub_y * 4 : hp.tiles_x * hp.tiles_y * 8;  // one per epilogue warp
-      LAUNCH_TRY(launch_finalize(h->plan->partials, records, nimg, npix, clip, 0, beta + b0,
+      LAUNCH_TRY(launch_finalize(h->plan->partials, records, nimg, npix, clip, correct_bias ? 1 : 0, beta + b0,
                                  l1 ? l1 + b0 : nullptr, st));
     }
   }
@@ -590,7 +607,7 @@ int filter_common_check(const void* img, int dtype, int kind, int B, int H, int 
 extern "C" {
 
 const char* wsu_last_error(void) { return g_err.c_str(); }
-int wsu_version(void) { return 100; }
+int wsu_version(void) { return 200; }
 int64_t wsu_launch_count(int reset) {
   const int64_t v = g_launches;
   if (reset) g_launches = 0;
@@ -887,18 +904,18 @@ int wsu_commit_weights(wsu_handle h) {
 
 int wsu_unet_forward(wsu_handle h, const void* x_dev, int x_dtype, float* y_dev, int B, int H, int W, void* stream) {
   if (!x_dev || !y_dev) return fail(WSU_ERR_INVALID, "null tensor pointer");
-  return unet_ws_device(h, x_dev, x_dtype, B, H, W, false, 0, 0, 0, nullptr, nullptr, y_dev, static_cast<cudaStream_t>(stream));
+  return unet_ws_device(h, x_dev, x_dtype, B, H, W, false, 0, 0, 0, 0, nullptr, nullptr, y_dev, static_cast<cudaStream_t>(stream));
 }
 
 int wsu_unet_ws_estimate(wsu_handle h, const void* img_dev, int img_dtype, int B, int H, int W, int weighted, int clip,
-                         int crop, float* beta_dev, float* l1_dev, float* yhat_dev, void* stream) {
+                         int crop, int correct_bias, float* beta_dev, float* l1_dev, float* yhat_dev, void* stream) {
   if (!img_dev || !beta_dev) return fail(WSU_ERR_INVALID, "null tensor pointer");
-  return unet_ws_device(h, img_dev, img_dtype, B, H, W, true, weighted, clip, crop, beta_dev, l1_dev, yhat_dev,
+  return unet_ws_device(h, img_dev, img_dtype, B, H, W, true, weighted, clip, crop, correct_bias, beta_dev, l1_dev, yhat_dev,
                         static_cast<cudaStream_t>(stream));
 }
 
 int wsu_unet_ws_estimate_host(wsu_handle h, const uint8_t* img_host, int B, int H, int W, int weighted, int clip, int crop,
-                              float* beta_host, float* l1_host) {
+                              int correct_bias, float* beta_host, float* l1_host) {
   if (!h) return fail(WSU_ERR_INVALID, "null handle");
   if (!img_host || !beta_host) return fail(WSU_ERR_INVALID, "null host pointer");
   int rc = check_shape(h, B, H, W);
@@ -938,8 +955,8 @@ int wsu_unet_ws_estimate_host(wsu_handle h, const uint8_t* img_host, int B, int 
                              h->s_copy));
     CUDA_TRY(cudaEventRecord(h->ev_in[slot], h->s_copy));
     CUDA_TRY(cudaStreamWaitEvent(h->s_comp, h->ev_in[slot], 0));
-    rc = unet_ws_device(h, h->stage_img[slot], WSU_U8, nimg, H, W, true, weighted, clip, crop, beta_dev + b0, l1_dev + b0, nullptr,
-                        h->s_comp);
+    rc = unet_ws_device(h, h->stage_img[slot], WSU_U8, nimg, H, W, true, weighted, clip, crop, correct_bias, beta_dev + b0,
+                        l1_dev + b0, nullptr, h->s_comp);
     if (rc) return rc;
     CUDA_TRY(cudaEventRecord(h->ev_free[slot], h->s_comp));
   }

@@ -321,7 +321,9 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
             s2 = float(i2);
           }
         }
-        ws_accumulate(acc, xv, xbar, xhat, ws_weight(p.weighted, s1, s2));
+        const float wgt = ws_weight(p.weighted, s1, s2);
+        if (p.bias_pass) acc.wb = fmaf(wgt * (xv - xbar), xhat, acc.wb);   // xhat = pixel_estimator(x_bar - x) here
+        else ws_accumulate(acc, xv, xbar, xhat, wgt);
       }
     }
   }
@@ -465,14 +467,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mma_kernel(const __grid_cons
       if (++acs == 2) { acs = 0; acph ^= 1; }
       if constexpr (EPI == EPI_HEAD) {
         if (p.partials) {
-          const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1);
+          const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1), wb = warp_sum(acc.wb);
           if (elect_one()) {
             const size_t tiles_per_img = size_t(p.tiles_x) * p.tiles_y;
             float* dst = p.partials + ((size_t(t.b) * tiles_per_img + t.tile_in_img) * 8 + (warp - 2)) * kPartialSlots;
-            dst[0] = wr;
-            dst[1] = w;
-            dst[2] = l1;
-            dst[3] = 0.f;
+            if (p.bias_pass) dst[3] = wb;
+            else { dst[0] = wr; dst[1] = w; dst[2] = l1; dst[3] = 0.f; }
           }
         }
       }
@@ -846,14 +846,12 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
                                               sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32);
         if constexpr (EPI == EPI_HEAD) {
           if (p.partials) {
-            const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1);
+            const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1), wb = warp_sum(acc.wb);
             if (elect_one()) {
               const size_t subs_per_img = size_t(p.sub_x) * p.sub_y;
               float* dst = p.partials + ((size_t(bc.b) * subs_per_img + bc.sub_in_img) * 4 + quad) * kPartialSlots;
-              dst[0] = wr;
-              dst[1] = w;
-              dst[2] = l1;
-              dst[3] = 0.f;
+              if (p.bias_pass) dst[3] = wb;
+              else { dst[0] = wr; dst[1] = w; dst[2] = l1; dst[3] = 0.f; }
             }
           }
         }
@@ -947,12 +945,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
     prefetch_tmap(&p.tmapH0);
     prefetch_tmap(&p.tmapH1);
     prefetch_tmap(&p.tmapW);
+    prefetch_tmap(&p.tmapW32);
     // a_full / w_full of the LEADER collect the bytes of both CTAs' TMA loads (cta_group::2 loads credit the leader's barrier)
     // after ONE arrival, the leader's own arrive.expect_tx for twice the per-CTA bytes: the peer issues its loads without
     // signalling first. (A remote mbarrier.arrive.release.cluster costs a GPU-scope fence, ~900 cycles: paid once per tap by
     // the weight relay it had made every layer with fewer than three MMAs per MAC wait on the relay, not on the tensor pipe.)
     for (int i = 0; i < C::SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < C::SW; ++i) { mbar_init(&w_full[i], (C::STACKED && leader) ? 2 : 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < C::SW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
     fence_mbar_init();
   }
@@ -987,7 +986,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
             const BoxCoord bc = decode_box(p, min(s0 + 2 * j + int(rank), p.total_sub - 1));
             mbar_wait(&a_empty[as], aph ^ 1);
             const uint32_t full_leader = mapa_u32(smem_u32(&a_full[as]), 0);
-            if (leader) mbar_arrive_expect_tx(&a_full[as], 2 * C::A_BYTES);
+            // source-0 blocks of a decoder layer under a reduced plan are ONE fp16 plane (half a box)
+            if (leader) mbar_arrive_expect_tx(&a_full[as], (src0 && p.src0_f16) ? C::A_BYTES : 2 * C::A_BYTES);
             tma_load_5d_2sm(sA + as * C::A_BYTES, tm, full_leader, ch, bc.x0, bc.y0, bc.b, 0);
             if (++as == C::SA) { as = 0; aph ^= 1; }
           }
@@ -1000,21 +1000,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
       int ws = 0;
       uint32_t wph = 0;
       const int chunks = p.cblocks * 9;
-      const uint32_t plane_bytes = N_TILE * 128;   // one (hi or lo) tile of the packed chunk
       for (int item = pair; item < items; item += npairs) {
         const int nt = item % p.n_tiles;
-        const uint8_t* wsrc = p.wpack + size_t(nt) * chunks * 2 * plane_bytes;
         for (int q = 0; q < chunks; ++q) {
-          const uint8_t* hi = wsrc + size_t(q) * 2 * plane_bytes;
-          const uint8_t* lo = hi + plane_bytes;
           uint8_t* dst = sW + ws * C::W_SLOT;
           mbar_wait(&w_empty[ws], wph ^ 1);
+          // the packed weights seen as rows of 128 B: 64- (or 32-) row boxes, raw copy (they are stored pre-swizzled)
           if constexpr (C::STACKED) {
-            mbar_arrive_expect_tx(&w_full[ws], C::W_BYTES);
-            bulk_load(dst, rank == 0 ? hi : lo, 8192, &w_full[ws]);                 // X: rows of [Whi; Wlo] owned by this CTA
-            bulk_load(dst + 8192, hi + rank * 4096, 4096, &w_full[ws]);            // Y: this CTA's half of Whi
+            const uint32_t full_leader = mapa_u32(smem_u32(&w_full[ws]), 0);
+            const int row0 = (nt * chunks + q) * 2 * N_TILE;                        // chunk = [Whi 64 rows][Wlo 64 rows]
+            if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * C::W_BYTES);
+            tma_load_2d_2sm(dst, &p.tmapW, full_leader, 0, row0 + int(rank) * 64);           // X: rank 0 Whi, rank 1 Wlo: [Whi; Wlo] over the pair
+            tma_load_2d_2sm(dst + 8192, &p.tmapW32, full_leader, 0, row0 + int(rank) * 32);  // Y: this CTA's half of Whi
           } else {
-            // the packed weights seen as rows of 128 B: 64-row boxes, raw copy (they are stored pre-swizzled)
             const uint32_t full_leader = mapa_u32(smem_u32(&w_full[ws]), 0);
             const int row_hi = (nt * chunks + q) * 2 * N_TILE + int(rank) * 64;
             if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * C::W_BYTES);
@@ -1027,20 +1025,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      if (!leader) {
-        // ===================================================== peer (stacked Cout = 64 variant only): relay weight arrivals
-        if constexpr (C::STACKED) {
-          int ws = 0;
-          uint32_t wph = 0;
-          for (int item = pair; item < items; item += npairs) {
-            for (int q = 0; q < p.cblocks * 9; ++q) {
-              mbar_wait(&w_full[ws], wph);
-              mbar_arrive_cluster(mapa_u32(smem_u32(&w_full[ws]), 0));
-              if (++ws == C::SW) { ws = 0; wph ^= 1; }
-            }
-          }
-        }
-      } else {
+      if (leader) {
         // ===================================================== leader: MMA issuer for the pair
         constexpr uint32_t idesc = TERMS == 3 ? make_idesc_bf16_m(256, N_TILE) : make_idesc_f16_m(256, N_TILE);
         int as = 0, ws = 0, acs = 0;
@@ -1052,55 +1037,68 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
           tc_fence_after();
           for (int c = 0; c < p.cblocks; ++c) {
             uint32_t a_slot[M_SUB];
-            for (int tap = 0; tap < 9; ++tap) {   // tap-major: with 64-cycle MMAs the ring slots turn over in time
-              const int wsl = ws;
-              mbar_wait(&w_full[ws], wph);
-              if (++ws == C::SW) { ws = 0; wph ^= 1; }
-              const uint32_t w_x = smem_u32(sW + wsl * C::W_SLOT), w_y = w_x + 8192;
-              const uint32_t tap_off = uint32_t((tap / 3) * (kHaloTW + 2) + (tap % 3)) * 128;
+            // F16 blocks (stacked Cout = 64 kernel only): source 0 of a decoder layer under a reduced plan, one fp16 plane
+            // against the fp16 [Whi; Wlo] tile = a single N=128 MMA per K step
+            auto issue_block = [&](auto f16_c) {
+              constexpr bool F16 = decltype(f16_c)::value;
+              for (int tap = 0; tap < 9; ++tap) {   // tap-major: with 64-cycle MMAs the ring slots turn over in time
+                const int wsl = ws;
+                mbar_wait(&w_full[ws], wph);
+                if (++ws == C::SW) { ws = 0; wph ^= 1; }
+                const uint32_t w_x = smem_u32(sW + wsl * C::W_SLOT), w_y = w_x + 8192;
+                const uint32_t tap_off = uint32_t((tap / 3) * (kHaloTW + 2) + (tap % 3)) * 128;
 #pragma unroll
-              for (int j = 0; j < M_SUB; ++j) {
-                if (j < nslot) {
-                  if (tap == 0) {
-                    mbar_wait(&a_full[as], aph);
-                    a_slot[j] = uint32_t(as);
-                    if (++as == C::SA) { as = 0; aph ^= 1; }
-                  }
-                  tc_fence_after();
-                  const uint64_t ad = make_sw128_desc(smem_u32(sA + a_slot[j] * C::A_BYTES), kHaloSBO);
-                  const uint64_t wxd = make_sw128_desc(w_x), wyd = make_sw128_desc(w_y);
-                  const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
+                for (int j = 0; j < M_SUB; ++j) {
+                  if (j < nslot) {
+                    if (tap == 0) {
+                      mbar_wait(&a_full[as], aph);
+                      a_slot[j] = uint32_t(as);
+                      if (++as == C::SA) { as = 0; aph ^= 1; }
+                    }
+                    tc_fence_after();
+                    const uint64_t ad = make_sw128_desc(smem_u32(sA + a_slot[j] * C::A_BYTES), kHaloSBO);
+                    const uint64_t wxd = make_sw128_desc(w_x), wyd = make_sw128_desc(w_y);
+                    const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    const uint64_t da_hi = desc_at(desc_lo(ad), desc_hi(ad), tap_off + k * 32);
-                    const uint64_t da_lo = desc_at(desc_lo(ad), desc_hi(ad), tap_off + kHaloRows * 128 + k * 32);
-                    const uint64_t dw_x = desc_at(desc_lo(wxd), desc_hi(wxd), k * 32);
-                    const uint64_t dw_y = desc_at(desc_lo(wyd), desc_hi(wyd), k * 32);
-                    if constexpr (TERMS == 2) {          // fp16 A x (Whi, Wlo): A read from shared memory once
-                      umma_bf16_2sm_a_fill(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
-                      umma_bf16_2sm_a_lastuse(d, da_hi, dw_y, idesc, 1);
-                    } else if constexpr (TERMS == 1) {   // fp16 A x fp16 W
-                      umma_bf16_2sm(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
-                    } else if constexpr (C::STACKED) {
-                      umma_bf16_2sm(d, da_hi, dw_x, make_idesc_bf16_m(256, 128), (c | tap | k) != 0);  // Ahi * [Whi; Wlo]
-                      umma_bf16_2sm(d, da_lo, dw_y, make_idesc_bf16_m(256, 64), 1);                    // Alo * Whi
-                    } else {
-                      if constexpr (COLL) {   // A_hi read once for its two products (compile-time: a runtime branch in this
-                                              // single-thread issue loop costs ~10 % of the layer)
+                    for (int k = 0; k < 4; ++k) {
+                      const uint64_t da_hi = desc_at(desc_lo(ad), desc_hi(ad), tap_off + k * 32);
+                      const uint64_t da_lo = desc_at(desc_lo(ad), desc_hi(ad), tap_off + kHaloRows * 128 + k * 32);
+                      const uint64_t dw_x = desc_at(desc_lo(wxd), desc_hi(wxd), k * 32);
+                      const uint64_t dw_y = desc_at(desc_lo(wyd), desc_hi(wyd), k * 32);
+                      if constexpr (F16) {                 // fp16 A x fp16 [Whi; Wlo]
+                        umma_bf16_2sm(d, da_hi, dw_x, make_idesc_f16_m(256, 128), (c | tap | k) != 0);
+                      } else if constexpr (TERMS == 2) {   // fp16 A x (Whi, Wlo): A read from shared memory once
                         umma_bf16_2sm_a_fill(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
                         umma_bf16_2sm_a_lastuse(d, da_hi, dw_y, idesc, 1);
-                        umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
-                      } else {
+                      } else if constexpr (TERMS == 1) {   // fp16 A x fp16 W
                         umma_bf16_2sm(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
-                        umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
-                        umma_bf16_2sm(d, da_hi, dw_y, idesc, 1);
+                      } else if constexpr (C::STACKED) {
+                        umma_bf16_2sm(d, da_hi, dw_x, make_idesc_bf16_m(256, 128), (c | tap | k) != 0);  // Ahi * [Whi; Wlo]
+                        umma_bf16_2sm(d, da_lo, dw_y, make_idesc_bf16_m(256, 64), 1);                    // Alo * Whi
+                      } else {
+                        if constexpr (COLL) {   // A_hi read once for its two products (compile-time: a runtime branch in this
+                                                // single-thread issue loop costs ~10 % of the layer)
+                          umma_bf16_2sm_a_fill(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
+                          umma_bf16_2sm_a_lastuse(d, da_hi, dw_y, idesc, 1);
+                          umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
+                        } else {
+                          umma_bf16_2sm(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
+                          umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
+                          umma_bf16_2sm(d, da_hi, dw_y, idesc, 1);
+                        }
                       }
                     }
+                    if (tap == 8) umma_commit_2sm(&a_empty[a_slot[j]], 3);
                   }
-                  if (tap == 8) umma_commit_2sm(&a_empty[a_slot[j]], 3);
                 }
+                umma_commit_2sm(&w_empty[wsl], 3);
               }
-              umma_commit_2sm(&w_empty[wsl], 3);
+            };
+            if constexpr (C::STACKED) {
+              if (p.src0_f16 && c < p.cblocks0) issue_block(std::true_type{});
+              else issue_block(std::false_type{});
+            } else {
+              issue_block(std::false_type{});
             }
           }
           umma_commit_2sm(&acc_full[acs], 3);
@@ -1136,14 +1134,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
                                                 sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32);
           if constexpr (EPI == EPI_HEAD) {
             if (p.partials) {
-              const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1);
+              const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1), wb = warp_sum(acc.wb);
               if (lane == 0) {
                 const size_t subs_per_img = size_t(p.sub_x) * p.sub_y;
                 float* dst = p.partials + ((size_t(bc.b) * subs_per_img + bc.sub_in_img) * 4 + quad) * kPartialSlots;
-                dst[0] = wr;
-                dst[1] = w;
-                dst[2] = l1;
-                dst[3] = 0.f;
+                if (p.bias_pass) dst[3] = wb;
+                else { dst[0] = wr; dst[1] = w; dst[2] = l1; dst[3] = 0.f; }
               }
             }
           }

@@ -16,6 +16,7 @@ struct alignas(64) ConvParams {
   CUtensorMap tmapH0;  // same sources with the haloed box (64 ch, 10, 18, 1 img, 2 planes) of the halo kernel
   CUtensorMap tmapH1;
   CUtensorMap tmapW;   // packed weights as rows of 128 B, box = 64 rows (CTA-pair kernels: each CTA loads its half of a tile)
+  CUtensorMap tmapW32; // same, box = 32 rows (stacked Cout = 64 pair kernel: half of the 64-row Whi tile)
   const uint8_t* wpack;  // packed + pre-swizzled split-bf16 weights, see pack_conv_weights()
   const float* bias;     // [Cout]
   int cblocks0;          // 64-channel blocks taken from source 0
@@ -60,6 +61,8 @@ struct alignas(64) ConvParams {
   float* partials;       // [B][tiles_per_img][4 warps][kPartialSlots]
   int weighted;          // WS_* mode
   int crop;              // 1: interior only (estimate.py:113-114), 0: whole image (losses.py:57-60)
+  int bias_pass;         // 1: this pass ran on the LSB-difference image; the head adds only sum w (x - x_bar) x_bias to slot 3 of
+                         // the partial records the first pass wrote (estimate.py:126-128)
 };
 
 // Bytes of one packed weight chunk (hi + lo tile) for an N_TILE-wide tile and one 64-deep K block.

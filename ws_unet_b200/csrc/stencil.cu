@@ -26,7 +26,9 @@ namespace {
 constexpr int kE11Seg = 128;   // pixels per row segment
 constexpr int kE11Rows = 8;    // rows per CTA (weights are loaded into registers once per CTA)
 
-template <bool kFloatIn, int CIN>
+// kIn: 0 = uint8 pixels (x / 255), 1 = float32 in [0,1], 2 = uint8 pixels, LSB DIFFERENCE image (x_bar - x) / 255 = +-1/255:
+// what the reference feeds the predictor for bias correction, pixel_estimator(x_bar - x) (src/ws/estimate.py:126-127)
+template <int kIn, int CIN>
 __global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict__ img, const float* __restrict__ w,
                                                          const float* __restrict__ bias, Act out, int segs_per_row,
                                                          int row_groups) {
@@ -48,7 +50,8 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict_
     xx = min(max(xx, 0), W - 1);                            // columns past a ragged last segment: any valid pixel
     const size_t o = ((size_t(b) * CIN + ci) * H + yy) * W + xx;
     float v;
-    if constexpr (kFloatIn) v = static_cast<const float*>(img)[o];
+    if constexpr (kIn == 1) v = static_cast<const float*>(img)[o];
+    else if constexpr (kIn == 2) v = __fdiv_rn((static_cast<const uint8_t*>(img)[o] & 1) ? -1.f : 1.f, 255.f);   // (x ^ 1) - x
     else v = __fdiv_rn(float(static_cast<const uint8_t*>(img)[o]), 255.f);  // x / 255. of src/unet/evaluate.py:45
     rows[ci][r][col] = v;
   }
@@ -973,18 +976,22 @@ __global__ void unpack_kernel(Act src, float* __restrict__ dst, int with_halo) {
 
 }  // namespace
 
-cudaError_t launch_first_conv(const void* img, int img_is_float, int cin, const float* w, const float* bias, Act out,
+cudaError_t launch_first_conv(const void* img, int img_kind, int cin, const float* w, const float* bias, Act out,
                               cudaStream_t stream) {
+  const bool img_is_float = img_kind == 1;
   if (cin == 1) {
     const int segs = (out.W + kE11Seg - 1) / kE11Seg;
     const int groups = (out.H + kE11Rows - 1) / kE11Rows;
     const int grid = out.B * groups * segs;
-    if (img_is_float)
-      first_conv_kernel<true, 1><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);
+    if (img_kind == 1)
+      first_conv_kernel<1, 1><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);
+    else if (img_kind == 2)
+      first_conv_kernel<2, 1><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);
     else
-      first_conv_kernel<false, 1><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);
+      first_conv_kernel<0, 1><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);
     return cudaGetLastError();
   }
+  if (img_kind == 2) return cudaErrorInvalidValue;   // the LSB-difference input exists for single-channel images only
   const size_t threads = size_t(out.B) * out.H * out.W * 8;
   const int grid = int((threads + 255) / 256);
   const size_t smem = (64 * cin * 9 + 64) * sizeof(float);

@@ -5,7 +5,8 @@
 
 namespace wsu {
 
-cudaError_t launch_first_conv(const void* img, int img_is_float, int cin, const float* w, const float* bias, Act out,
+// img_kind: 0 uint8 pixels, 1 float32 in [0,1], 2 uint8 pixels read as the LSB-difference image (x_bar - x) / 255
+cudaError_t launch_first_conv(const void* img, int img_kind, int cin, const float* w, const float* bias, Act out,
                               cudaStream_t stream);
 int filter_ws_strips(int H);
 // register sliding-window fast path (uint8, KB/AVG, no bias term, no x_hat output, W % 4 == 0)

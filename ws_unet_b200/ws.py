@@ -67,27 +67,16 @@ def ws_estimate(images: torch.Tensor, predictor, weighted: int = 0, clip: bool =
             pred = filters.filter_predict(images, predictor) if return_prediction else None
         elif isinstance(predictor, UNet):
             h = predictor.native_handle(dev)
-            yhat = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev) if (return_prediction or correct_bias) else None
-            if not correct_bias:
-                _native.check(lib.wsu_unet_ws_estimate(
-                    h, ctypes.c_void_p(images.data_ptr()), dtype, B, H, W, int(weighted), int(bool(clip)), int(crop),
-                    ctypes.c_void_p(beta.data_ptr()), l1_ptr,
-                    ctypes.c_void_p(yhat.data_ptr()) if yhat is not None else None, st), 'wsu_unet_ws_estimate')
-            else:
-                # estimate.py:126-128: second predictor pass on the difference image x_bar - x (values +-1),
-                # which infere_single scales by 1/255 like any other input (src/unet/evaluate.py:45)
-                if dtype != _native.WSU_U8:
-                    raise ValueError("correct_bias needs uint8 images")
-                _native.check(lib.wsu_unet_forward(h, ctypes.c_void_p(images.data_ptr()), dtype,
-                                                   ctypes.c_void_p(yhat.data_ptr()), B, H, W, st), 'wsu_unet_forward')
-                diff = ((images ^ 1).to(torch.float32) - images.to(torch.float32)) / 255.
-                ybias = predictor(diff)
-                xhat = yhat * 255.
-                xbias = ybias * 255.
-                _native.check(lib.wsu_ws_from_prediction(
-                    dev.index, ctypes.c_void_p(images.data_ptr()), dtype, ctypes.c_void_p(xhat.data_ptr()), 0,
-                    ctypes.c_void_p(xbias.data_ptr()), int(weighted), int(bool(clip)), int(crop),
-                    ctypes.c_void_p(beta.data_ptr()), l1_ptr, B, H, W, st), 'wsu_ws_from_prediction')
+            yhat = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev) if return_prediction else None
+            if correct_bias and dtype != _native.WSU_U8:
+                raise ValueError("correct_bias needs uint8 images")
+            # correct_bias (estimate.py:126-128): the library runs the predictor a second time on the LSB-difference image
+            # x_bar - x (formed inside the first-layer kernel, scaled by 1/255 like any input, src/unet/evaluate.py:45) and its
+            # head accumulates sum w (x - x_bar) x_bias next to the first pass's sums - one C call, no prediction map in HBM
+            _native.check(lib.wsu_unet_ws_estimate(
+                h, ctypes.c_void_p(images.data_ptr()), dtype, B, H, W, int(weighted), int(bool(clip)), int(crop),
+                int(bool(correct_bias)), ctypes.c_void_p(beta.data_ptr()), l1_ptr,
+                ctypes.c_void_p(yhat.data_ptr()) if yhat is not None else None, st), 'wsu_unet_ws_estimate')
             pred = yhat
         else:
             raise TypeError("predictor must be a ws_unet_b200 UNet or one of " + str(list(_native.PRED_KINDS)))
@@ -123,11 +112,9 @@ def ws_estimate_host(images: torch.Tensor, predictor, weighted: int = 0, clip: b
                 int(bool(correct_bias)), ctypes.c_void_p(beta.data_ptr()), ctypes.c_void_p(l1.data_ptr()) if return_l1 else None,
                 B, H, W), 'wsu_filter_ws_estimate_host')
         elif isinstance(predictor, UNet):
-            if correct_bias:
-                raise NotImplementedError("correct_bias with a UNet predictor: use ws_estimate on device tensors")
             _native.check(lib.wsu_unet_ws_estimate_host(
                 predictor.native_handle(dev), ctypes.c_void_p(images.data_ptr()), B, H, W, int(weighted), int(bool(clip)), 1,
-                ctypes.c_void_p(beta.data_ptr()), ctypes.c_void_p(l1.data_ptr()) if return_l1 else None),
+                int(bool(correct_bias)), ctypes.c_void_p(beta.data_ptr()), ctypes.c_void_p(l1.data_ptr()) if return_l1 else None),
                 'wsu_unet_ws_estimate_host')
         else:
             raise TypeError("predictor must be a ws_unet_b200 UNet or one of " + str(list(_native.PRED_KINDS)))

@@ -114,6 +114,18 @@ int wsu_ws_from_prediction(int device, const void* img_dev, int img_dtype, const
 int wsu_ws_grad_prediction(int device, const void* img_dev, int img_dtype, const float* coef_dev, int crop, float scale,
                            float* grad_dev, int B, int H, int W, void* stream);
 
+/* UniformDropout.forward (src/unet/model/unet.py:32-42): out = x * mask + KB(reflect-padded x) * (1 - mask) on the channels
+ * whose bit is set in channel_mask, a copy elsewhere. x_dev (B,C,H,W) float32 in [0,1] or uint8 pixels (scaled by 1/255);
+ * mask_dev (B,1,H,W) float32 of 0 / 1 (the caller draws it); out_dev (B,C,H,W) float32. */
+int wsu_uniform_dropout(int device, const void* x_dev, int x_dtype, const float* mask_dev, float* out_dev, int B, int C,
+                        int H, int W, uint32_t channel_mask, void* stream);
+
+/* Matrix form of the linear predictors (src/filters/evaluate.py:53-76 get_filter_residuals over the N x 9 neighbour matrix
+ * of src/_defs/filters.py:39-69): resid[i] = mat[i][8] - sum_k coef[k] * mat[i][k], accumulated in float64 left to right.
+ * mat_dtype: 0 uint8, 1 float32, 2 float64; coef_dev 8 doubles; resid_dev n_rows doubles. */
+int wsu_filter_residual_rows(int device, const void* mat_dev, int mat_dtype, const double* coef_dev, double* resid_dev,
+                             int64_t n_rows, void* stream);
+
 /* ---- introspection for the per-layer parity tests: copy a feature map of the LAST micro-batch of the last forward
  * as float32 NCHW (hi+lo recombined). name in {"e11","e12","p1","e21",...,"u3","d31","d32",...}. with_halo=1 returns
  * (B,C,H+2,W+2) including the materialised reflect border. dims_out receives (B,C,H,W) of the returned tensor. */

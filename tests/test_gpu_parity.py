@@ -68,6 +68,7 @@ def test_unet_layers_and_reflect_halo_match_oracle(cuda_dev):
     x = np.random.default_rng(3).random((2, 1, 48, 80), dtype=np.float32)
     lib = _native.load()
     _native.check(lib.wsu_set_option(m.native_handle(cuda_dev), b'fuse_e11', 0))   # materialise e11 so it can be inspected
+    _native.check(lib.wsu_set_option(m.native_handle(cuda_dev), b'alias_buffers', 0))   # every map keeps its own bytes
     m(torch.from_numpy(x).to(cuda_dev))
     _, acts = uo.unet_forward(sd, x, 2, keep=True)
     for name in ['e11', 'e12', 'p1', 'e21', 'e22', 'p2', 'e31', 'e32', 'u3', 'd31', 'd32', 'u4', 'd41']:
@@ -363,6 +364,27 @@ def test_kernel_variants_agree(cuda_dev):
         _native.check(lib.wsu_set_option(h, b'no_such_option', 1))
 
 
+def test_buffer_aliasing_is_invisible(cuda_dev):
+    """Feature maps with disjoint lifetimes share arena bytes (default); with aliasing off every map has its own range.
+    Results are bit-identical, the arena shrinks."""
+    import ws_unet_b200 as W
+    from ws_unet_b200 import _native
+    lib = _native.load()
+    img = torch.randint(0, 256, (5, 1, 64, 96), dtype=torch.uint8, device=cuda_dev)
+    for nsteps in (0, 1, 2, 3):
+        m = _model(nsteps, 30 + nsteps, cuda_dev)
+        h = m.native_handle(cuda_dev)
+        out, size = {}, {}
+        for alias in (1, 0):
+            _native.check(lib.wsu_set_option(h, b'alias_buffers', alias))
+            out[alias] = W.ws_estimate(img, m, weighted=1, clip=False, return_l1=True, return_prediction=True)
+            v = ctypes.c_int64()
+            _native.check(lib.wsu_get_info(h, b'bytes_per_image', ctypes.byref(v)))
+            size[alias] = v.value
+        assert all(torch.equal(a, b) for a, b in zip(out[0], out[1]))
+        assert size[1] <= size[0] and (nsteps == 0 or size[1] < 0.7 * size[0]), (nsteps, size)
+
+
 def test_weight_updates_are_picked_up(cuda_dev):
     """load_state_dict / in-place edits (disable_center_pixels, unet.py:196-199) must reach the packed device weights."""
     m = _model(2, 3, cuda_dev)
@@ -415,7 +437,17 @@ def test_uniform_dropout_blend(cuda_dev):
     x_kb = torch.nn.functional.conv2d(torch.nn.functional.pad(x, (1, 1, 1, 1), mode='reflect'), kb)
     blended = x * mask + x_kb * (1 - mask)
     m.input_dropout.p = 1  # identity from here on: forward(blended) must reproduce y
-    assert torch.equal(m(blended), y)
+    # the library's KB stencil sums in a fixed order, torch's conv2d in its own: inputs agree to an ulp, outputs to 1e-6
+    assert (m(blended) - y).abs().max().item() < 1e-6
+    # uint8 input: scaled by 1/255 inside the kernel; the caller's tensor stays untouched
+    m.input_dropout.p = 0.5
+    x8 = torch.randint(0, 256, (2, 1, 32, 32), dtype=torch.uint8, device=cuda_dev)
+    y8 = m(x8)
+    mask8 = m.input_dropout.mask
+    xf = x8.float() / 255.
+    ref8 = xf * mask8 + torch.nn.functional.conv2d(torch.nn.functional.pad(xf, (1, 1, 1, 1), mode='reflect'), kb) * (1 - mask8)
+    m.input_dropout.p = 1
+    assert (m(ref8) - y8).abs().max().item() < 1e-6
 
 
 def test_host_buffer_entry_points(cuda_dev):

@@ -46,6 +46,7 @@ def test_reduced_plan_layers_and_halo(cuda_dev, mode):
     m = _model(2, 9, cuda_dev, mode)
     x = np.random.default_rng(3).random((2, 1, 48, 80), dtype=np.float32)
     lib = _native.load()
+    _native.check(lib.wsu_set_option(m.native_handle(cuda_dev), b'alias_buffers', 0))   # every map keeps its own bytes
     m(torch.from_numpy(x).to(cuda_dev))
     _, acts = uo.unet_forward(sd, x, 2, keep=True)
     for name in ['e11', 'e12', 'p1', 'e21', 'e22', 'p2', 'e31', 'e32', 'u3', 'd31', 'd32', 'u4', 'd41']:

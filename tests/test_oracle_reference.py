@@ -102,3 +102,13 @@ def test_list_files_matches_fabrika_selection():
     assert all(D._resolve_case(REF / 'data' / n).exists() for n in st['name'])
     st2 = D.list_files(REF / 'data', stego_method='HILLR', alpha=0.05, take_num_images=2)
     assert len(st2) == 2
+    # split=: a CSV inside the dataset replaces the globbed files.csv tables (src/fabrika.py:51-52)
+    import pandas as pd
+    import tempfile, pathlib
+    with tempfile.TemporaryDirectory() as td:
+        td = pathlib.Path(td)
+        pd.DataFrame({'name': ['images/b.png', 'images/a.png', 'stego/x.png'], 'stego_method': [None, None, 'LSBR'],
+                      'alpha': [None, None, 0.4], 'device': ['007', '007', '007']}).to_csv(td / 'split_te.csv', index=False)
+        assert D.list_files(td, split='split_te.csv')['name'].tolist() == ['images/a.png', 'images/b.png']
+        assert D.list_files(td, split='split_te.csv', stego_method='LSBR', alpha=0.4)['name'].tolist() == ['stego/x.png']
+        assert D.list_files(td, split='split_te.csv')['device'].tolist() == ['007', '007']

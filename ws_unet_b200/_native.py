@@ -37,6 +37,8 @@ PROTOTYPES = {
     "wsu_filter_ws_estimate_host": (_i, [_i, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i]),
     "wsu_ws_from_prediction": (_i, [_i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp]),
     "wsu_ws_grad_prediction": (_i, [_i, _vp, _i, _vp, _i, _c.c_float, _vp, _i, _i, _i, _vp]),
+    "wsu_uniform_dropout": (_i, [_i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _c.c_uint32, _vp]),
+    "wsu_filter_residual_rows": (_i, [_i, _vp, _i, _vp, _vp, _i64, _vp]),
     "wsu_debug_layer": (_i, [_vp, _c.c_char_p, _vp, _sz, _i, _c.POINTER(_i64), _vp]),
     "wsu_get_info": (_i, [_vp, _c.c_char_p, _c.POINTER(_i64)]),
     "wsu_profile_read": (_i, [_vp, _vp, _i]),

@@ -163,6 +163,7 @@ struct Plan {  // everything that depends on (micro-batch, H, W)
   std::map<std::string, Act> acts;
   std::vector<void*> allocs;
   float* partials = nullptr;
+  size_t arena_bytes = 0;
   int tiles_per_img = 0;
   std::vector<std::pair<ConvParams, std::pair<int, int>>> convs;  // params, (n_tile, epi); head is the last entry
   std::vector<std::string> conv_names;
@@ -215,6 +216,7 @@ struct wsu_context {
   // fp16 (hi, lo) / fp16 hi-only weights = 2 / 1 MMAs per MAC and half the activation bytes; the full-resolution layers
   // (e12, d41, d42), whose rounding reaches the output directly, stay three-term. Whether a plan keeps a given model inside
   // the 1e-3 px bar depends on its weights: UNet.calibrate_precision() measures it against plan 0 and picks.
+  bool alias_buffers = true;  // option "alias_buffers": feature maps with disjoint lifetimes share arena bytes
   int precision = 0;
   int precision_active = 0;   // what commit could honour (needs resident up-convolutions: unet_1, unet_2)
   bool use_upres = true;  // transposed convs through upconv_res_kernel (option "upconv_resident")
@@ -234,39 +236,77 @@ void free_plan(Plan* p) {
   p->allocs.clear();
 }
 
-int alloc_act(Plan& pl, const std::string& name, int B, int H, int W, int C, int fmt, cudaStream_t st) {
+// Feature maps are carved out of ONE arena. A map lives from the step that writes it to the last step that reads it; maps
+// whose lifetimes do not overlap share bytes (first-fit over the maps alive at the newcomer's birth). With "alias_buffers"
+// off (tests that inspect every layer after a pass) every map keeps its own range.
+struct ActDecl {
+  std::string name;
   Act a;
-  a.B = B; a.H = H; a.W = W; a.C = C;
-  a.fmt = fmt;
-  a.plane = act_plane_elems(B, H, W, C);
-  void* p = nullptr;
-  const size_t bytes = a.plane * (fmt == ACT_F16 ? 1 : 2) * sizeof(__nv_bfloat16);
-  cudaError_t e = cudaMalloc(&p, bytes);
-  if (e != cudaSuccess) return fail(WSU_ERR_CUDA, "cudaMalloc(" + name + ", " + std::to_string(bytes) + " B): " + cudaGetErrorString(e));
-  pl.allocs.push_back(p);
-  // borders that no producer writes (none today) and overhanging reads stay finite. Zero-filled ON THE CALLER'S STREAM:
-  // the chain kernels run there, and a non-blocking stream does not order itself behind a legacy-stream memset.
-  e = cudaMemsetAsync(p, 0, bytes, st);
-  if (e != cudaSuccess) return fail(WSU_ERR_CUDA, "cudaMemsetAsync(" + name + "): " + cudaGetErrorString(e));
-  a.base = static_cast<__nv_bfloat16*>(p);
-  pl.acts[name] = a;
+  size_t bytes = 0, offset = 0;
+  int birth = 0, death = 0;
+};
+
+int declare_act(std::vector<ActDecl>& decls, const std::string& name, int B, int H, int W, int C, int fmt) {
+  ActDecl d;
+  d.name = name;
+  d.a.B = B; d.a.H = H; d.a.W = W; d.a.C = C;
+  d.a.fmt = fmt;
+  d.a.plane = act_plane_elems(B, H, W, C);
+  d.a.base = nullptr;
+  d.bytes = ((d.a.plane * (fmt == ACT_F16 ? 1 : 2) * sizeof(__nv_bfloat16)) + 1023) & ~size_t(1023);   // TMA / swizzle friendly
+  d.birth = -1;
+  d.death = -1;
+  decls.push_back(d);
   return WSU_OK;
 }
 
-size_t per_image_bytes(int nsteps, int H, int W, bool deep_f16) {
+size_t layout_acts(std::vector<ActDecl>& decls, bool alias) {
+  std::vector<size_t> order(decls.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return decls[x].birth < decls[y].birth; });
   size_t total = 0;
-  auto add = [&](int l, int c, bool f16) { total += size_t(H >> l) * (W >> l) * c * (f16 ? 2 : 4); };
-  for (int l = 0; l <= nsteps; ++l) {
-    add(l, chan(l), deep_f16 && l >= 1);
-    add(l, chan(l), deep_f16 && l >= 1);
-    if (l < nsteps) add(l + 1, chan(l), deep_f16);
+  std::vector<size_t> placed;
+  for (size_t oi : order) {
+    ActDecl& d = decls[oi];
+    size_t off = 0;
+    if (!alias) {
+      off = total;
+    } else {
+      // lowest offset whose range is free of every map still alive when this one is written (a step's inputs are alive
+      // while it writes: death >= birth counts as overlap)
+      bool moved = true;
+      while (moved) {
+        moved = false;
+        for (size_t pj : placed) {
+          const ActDecl& q = decls[pj];
+          const bool time_overlap = !(q.death < d.birth || d.death < q.birth);
+          if (time_overlap && off < q.offset + q.bytes && q.offset < off + d.bytes) { off = q.offset + q.bytes; moved = true; }
+        }
+      }
+    }
+    d.offset = off;
+    total = std::max(total, off + d.bytes);
+    placed.push_back(oi);
   }
-  for (int l = nsteps - 1; l >= 0; --l) {
-    add(l, chan(l), deep_f16);               // up-convolution output
-    add(l, chan(l), deep_f16 && l >= 1);
-    if (l > 0) add(l, chan(l), deep_f16);
+  return total;
+}
+
+int place_acts(Plan& pl, std::vector<ActDecl>& decls, bool alias, cudaStream_t st) {
+  const size_t total = layout_acts(decls, alias);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, total);
+  if (e != cudaSuccess) return fail(WSU_ERR_CUDA, "cudaMalloc(feature-map arena, " + std::to_string(total) + " B): " + cudaGetErrorString(e));
+  pl.allocs.push_back(p);
+  pl.arena_bytes = total;
+  // overhanging reads stay finite. Zero-filled ON THE CALLER'S STREAM: the chain kernels run there, and a non-blocking
+  // stream does not order itself behind a legacy-stream memset.
+  e = cudaMemsetAsync(p, 0, total, st);
+  if (e != cudaSuccess) return fail(WSU_ERR_CUDA, std::string("cudaMemsetAsync(arena): ") + cudaGetErrorString(e));
+  for (ActDecl& d : decls) {
+    d.a.base = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(p) + d.offset);
+    pl.acts[d.name] = d.a;
   }
-  return total + total / 8;
+  return WSU_OK;
 }
 
 // Build a conv step. src1 may be null (no concat).
@@ -365,68 +405,85 @@ int build_plan(wsu_context* h, int mb, int H, int W, cudaStream_t st) {
   return rc;
 }
 
-int build_plan_impl(wsu_context* h, int mb, int H, int W, cudaStream_t st) {
-  Plan& pl = *h->plan;
-  pl.mb = mb; pl.H = H; pl.W = W;
+struct Step { std::string layer, src0, src1, out, pool; bool up, relu; int epi; };
+
+// feature maps (with lifetimes) and layer steps of one pass over `mb` images of H x W
+void describe_chain(const wsu_context* h, int mb, int H, int W, std::vector<ActDecl>& decls, std::vector<Step>& steps) {
   const int n = h->nsteps;
-  int rc;
   // activations. Under a reduced-precision plan every map at level >= 1 (and every up-convolution output) is read only by
   // one-/two-term layers or channel blocks and is stored as ONE fp16 plane; e11, e12, d41 feed three-term layers and stay
   // split-bf16.
   auto fmt_at = [&](int level) { return (h->precision_active != 0 && level >= 1) ? int(ACT_F16) : int(ACT_SPLIT); };
   for (int l = 0; l <= n; ++l) {
     const int hh = H >> l, ww = W >> l;
-    if ((rc = alloc_act(pl, enc_name(l, 1), mb, hh, ww, chan(l), fmt_at(l), st))) return rc;
-    if (!(n == 0)) {
-      if ((rc = alloc_act(pl, enc_name(l, 2), mb, hh, ww, chan(l), fmt_at(l), st))) return rc;
-    }
-    if (l < n) {
-      if ((rc = alloc_act(pl, "p" + std::to_string(l + 1), mb, hh / 2, ww / 2, chan(l), fmt_at(l + 1), st))) return rc;
-    }
+    declare_act(decls, enc_name(l, 1), mb, hh, ww, chan(l), fmt_at(l));
+    if (!(n == 0)) declare_act(decls, enc_name(l, 2), mb, hh, ww, chan(l), fmt_at(l));
+    if (l < n) declare_act(decls, "p" + std::to_string(l + 1), mb, hh / 2, ww / 2, chan(l), fmt_at(l + 1));
   }
   for (int l = n - 1; l >= 0; --l) {
     const int hh = H >> l, ww = W >> l;
     // up-convolution outputs are fp16 at every level (u4 feeds d41's two-term source-0 blocks); their bias is folded
     // into the consuming layer's bias at commit, which keeps the stored values small and their rounding harmless
-    if ((rc = alloc_act(pl, "u" + std::to_string(4 - l), mb, hh, ww, chan(l), fmt_at(l + 1), st))) return rc;
-    if ((rc = alloc_act(pl, dec_name(l, 1), mb, hh, ww, chan(l), fmt_at(l), st))) return rc;
-    if (l > 0) {
-      if ((rc = alloc_act(pl, dec_name(l, 2), mb, hh, ww, chan(l), fmt_at(l), st))) return rc;
-    }
+    declare_act(decls, "u" + std::to_string(4 - l), mb, hh, ww, chan(l), fmt_at(l + 1));
+    declare_act(decls, dec_name(l, 1), mb, hh, ww, chan(l), fmt_at(l));
+    if (l > 0) declare_act(decls, dec_name(l, 2), mb, hh, ww, chan(l), fmt_at(l));
   }
-  // layer chain (first conv is launched separately)
-  auto A = [&](const std::string& s) -> Act& { return pl.acts.at(s); };
+  // layer chain (first conv = step 0 is launched separately); "" = no such tensor
   for (int l = 0; l <= n; ++l) {
-    if (l > 0) {
-      if ((rc = add_conv(h, pl, enc_name(l, 1), h->layers.at(enc_name(l, 1)), A("p" + std::to_string(l)), nullptr, &A(enc_name(l, 1)), nullptr,
-                         false, true, EPI_ACT)))
-        return rc;
-    }
-    if (n == 0) {
-      if ((rc = add_conv(h, pl, enc_name(0, 2), h->layers.at(enc_name(0, 2)), A(enc_name(0, 1)), nullptr, nullptr, nullptr, false, true, EPI_HEAD)))
-        return rc;
-    } else {
-      const Act* pool = (l < n) ? &A("p" + std::to_string(l + 1)) : nullptr;
-      if ((rc = add_conv(h, pl, enc_name(l, 2), h->layers.at(enc_name(l, 2)), A(enc_name(l, 1)), nullptr, &A(enc_name(l, 2)), pool, false, true,
-                         EPI_ACT)))
-        return rc;
-    }
+    if (l > 0) steps.push_back({enc_name(l, 1), "p" + std::to_string(l), "", enc_name(l, 1), "", false, true, EPI_ACT});
+    if (n == 0) steps.push_back({enc_name(0, 2), enc_name(0, 1), "", "", "", false, true, EPI_HEAD});
+    else steps.push_back({enc_name(l, 2), enc_name(l, 1), "", enc_name(l, 2), (l < n) ? "p" + std::to_string(l + 1) : "", false, true, EPI_ACT});
   }
   for (int l = n - 1; l >= 0; --l) {
     const std::string below = (l + 1 == n) ? enc_name(l + 1, 2) : dec_name(l + 1, 2);
     const std::string u = "u" + std::to_string(4 - l);
-    if ((rc = add_conv(h, pl, up_name(l), h->layers.at(up_name(l)), A(below), nullptr, &A(u), nullptr, true, false, EPI_ACT))) return rc;
-    if ((rc = add_conv(h, pl, dec_name(l, 1), h->layers.at(dec_name(l, 1)), A(u), &A(enc_name(l, 2)), &A(dec_name(l, 1)), nullptr, false, true,
-                       EPI_ACT)))
+    steps.push_back({up_name(l), below, "", u, "", true, false, EPI_ACT});
+    steps.push_back({dec_name(l, 1), u, enc_name(l, 2), dec_name(l, 1), "", false, true, EPI_ACT});
+    if (l > 0) steps.push_back({dec_name(l, 2), dec_name(l, 1), "", dec_name(l, 2), "", false, true, EPI_ACT});
+    else steps.push_back({dec_name(l, 2), dec_name(l, 1), "", "", "", false, true, EPI_HEAD});
+  }
+  auto decl_of = [&](const std::string& nm) -> ActDecl* {
+    for (ActDecl& d : decls) if (d.name == nm) return &d;
+    return nullptr;
+  };
+  auto touch = [&](const std::string& nm, int t, bool write) {
+    if (nm.empty()) return;
+    ActDecl* d = decl_of(nm);
+    if (write && d->birth < 0) d->birth = t;
+    d->death = std::max(d->death, t);
+  };
+  touch(enc_name(0, 1), 0, true);
+  for (size_t i = 0; i < steps.size(); ++i) {
+    const int t = int(i) + 1;
+    touch(steps[i].src0, t, false);
+    touch(steps[i].src1, t, false);
+    touch(steps[i].out, t, true);
+    touch(steps[i].pool, t, true);
+  }
+  for (ActDecl& d : decls) if (d.birth < 0) { d.birth = 0; d.death = int(steps.size()) + 1; }   // never written: keep apart
+}
+
+// feature-map bytes of one image under the current options (what the micro-batch budget divides)
+size_t per_image_bytes(const wsu_context* h, int H, int W) {
+  std::vector<ActDecl> decls;
+  std::vector<Step> steps;
+  describe_chain(h, 1, H, W, decls, steps);
+  return layout_acts(decls, h->alias_buffers);
+}
+
+int build_plan_impl(wsu_context* h, int mb, int H, int W, cudaStream_t st) {
+  Plan& pl = *h->plan;
+  pl.mb = mb; pl.H = H; pl.W = W;
+  int rc;
+  std::vector<ActDecl> decls;
+  std::vector<Step> steps;
+  describe_chain(h, mb, H, W, decls, steps);
+  if ((rc = place_acts(pl, decls, h->alias_buffers, st))) return rc;
+  auto A = [&](const std::string& s) -> Act& { return pl.acts.at(s); };
+  for (const Step& sp : steps) {
+    if ((rc = add_conv(h, pl, sp.layer, h->layers.at(sp.layer), A(sp.src0), sp.src1.empty() ? nullptr : &A(sp.src1),
+                       sp.out.empty() ? nullptr : &A(sp.out), sp.pool.empty() ? nullptr : &A(sp.pool), sp.up, sp.relu, sp.epi)))
       return rc;
-    if (l > 0) {
-      if ((rc = add_conv(h, pl, dec_name(l, 2), h->layers.at(dec_name(l, 2)), A(dec_name(l, 1)), nullptr, &A(dec_name(l, 2)), nullptr, false, true,
-                         EPI_ACT)))
-        return rc;
-    } else {
-      if ((rc = add_conv(h, pl, dec_name(l, 2), h->layers.at(dec_name(l, 2)), A(dec_name(l, 1)), nullptr, nullptr, nullptr, false, true, EPI_HEAD)))
-        return rc;
-    }
   }
   void* pp = nullptr;
   CUDA_TRY(cudaMalloc(&pp, size_t(mb) * pl.tiles_per_img * 4 * kPartialSlots * sizeof(float)));
@@ -448,7 +505,7 @@ int check_shape(wsu_context* h, int B, int H, int W) {
 int pick_micro_batch(wsu_context* h, int B, int H, int W) {
   if (h->micro_batch > 0) return int(std::min<int64_t>(h->micro_batch, B));
   const size_t budget = size_t(20) << 30;
-  int mb = int(std::max<size_t>(1, budget / per_image_bytes(h->nsteps, H, W, h->precision_active != 0)));
+  int mb = int(std::max<size_t>(1, budget / per_image_bytes(h, H, W)));
   mb = std::min(std::min(mb, 64), B);
   // even passes: avoid a short ragged tail pass (e.g. B=256 -> 8 x 32 instead of 7 x 33 + 25)
   const int passes = (B + mb - 1) / mb;
@@ -705,6 +762,13 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
     if (h->precision != int(value)) {
       h->precision = int(value);
       if (h->committed) return wsu_commit_weights(h);   // weights are packed per plan (bf16 or fp16 pairs); drops the shape plan too
+    }
+    return WSU_OK;
+  }
+  if (!std::strcmp(key, "alias_buffers")) {
+    if (h->alias_buffers != (value != 0)) {
+      h->alias_buffers = value != 0;
+      if (h->plan) { cudaDeviceSynchronize(); free_plan(h->plan.get()); h->plan.reset(); }
     }
     return WSU_OK;
   }
@@ -1133,13 +1197,33 @@ int wsu_ws_from_prediction(int device, const void* img_dev, int img_dtype, const
   return WSU_OK;
 }
 
+int wsu_uniform_dropout(int device, const void* x_dev, int x_dtype, const float* mask_dev, float* out_dev, int B, int C,
+                        int H, int W, uint32_t channel_mask, void* stream) {
+  if (!x_dev || !mask_dev || !out_dev) return fail(WSU_ERR_INVALID, "null tensor pointer");
+  if (x_dtype != WSU_U8 && x_dtype != WSU_F32) return fail(WSU_ERR_INVALID, "dtype must be WSU_U8 or WSU_F32");
+  if (B <= 0 || C <= 0 || C > 32 || H < 2 || W < 2) return fail(WSU_ERR_INVALID, "need B >= 1, 1 <= C <= 32 and H, W >= 2 (reflect padding)");
+  DEVICE_SCOPE(device);
+  LAUNCH_TRY(launch_kb_blend(x_dev, x_dtype == WSU_F32, mask_dev, out_dev, B, C, H, W, channel_mask, static_cast<cudaStream_t>(stream)));
+  return WSU_OK;
+}
+
+int wsu_filter_residual_rows(int device, const void* mat_dev, int mat_dtype, const double* coef_dev, double* resid_dev,
+                             int64_t n_rows, void* stream) {
+  if (!mat_dev || !coef_dev || !resid_dev) return fail(WSU_ERR_INVALID, "null tensor pointer");
+  if (mat_dtype < 0 || mat_dtype > 2) return fail(WSU_ERR_INVALID, "mat_dtype must be 0 (uint8), 1 (float32) or 2 (float64)");
+  if (n_rows <= 0) return fail(WSU_ERR_INVALID, "n_rows must be positive");
+  DEVICE_SCOPE(device);
+  LAUNCH_TRY(launch_residual_matvec(mat_dev, mat_dtype, coef_dev, resid_dev, n_rows, static_cast<cudaStream_t>(stream)));
+  return WSU_OK;
+}
+
 int wsu_get_info(wsu_handle h, const char* key, int64_t* out) {
   if (!h || !key || !out) return fail(WSU_ERR_INVALID, "null argument");
   if (!std::strcmp(key, "micro_batch")) *out = h->plan ? h->plan->mb : 0;
   else if (!std::strcmp(key, "last_images")) *out = h->last_nimg;
   else if (!std::strcmp(key, "num_sms")) *out = h->num_sms;
   else if (!std::strcmp(key, "precision")) *out = h->precision_active;
-  else if (!std::strcmp(key, "bytes_per_image")) *out = h->plan ? int64_t(per_image_bytes(h->nsteps, h->plan->H, h->plan->W, h->precision_active != 0)) : 0;
+  else if (!std::strcmp(key, "bytes_per_image")) *out = h->plan ? int64_t(h->plan->arena_bytes / size_t(h->plan->mb)) : 0;
   else if (!std::strcmp(key, "layers")) *out = h->plan ? int64_t(h->plan->convs.size()) + 1 : 0;
   else return fail(WSU_ERR_INVALID, std::string("unknown info key ") + key);
   return WSU_OK;

@@ -936,6 +936,55 @@ __global__ void finalize_kernel(const float* __restrict__ partials, int records,
   }
 }
 
+// ------------------------------------------------------------------------------------------------ UniformDropout blend
+// src/unet/model/unet.py:32-42: every pixel of the dropped channels is kept with probability 1 - drop_rate (mask = 1) and
+// otherwise replaced by its KB prediction over the reflect-padded channel: out = x * mask + KB(x) * (1 - mask).
+// x: (B,C,H,W) float32 in [0,1] or uint8 pixels (scaled by 1/255 first, src/unet/evaluate.py:45); mask: (B,1,H,W) of 0 / 1;
+// chan_mask bit c set = channel c is a dropped channel; other channels are copied.
+template <bool kFloatIn>
+__global__ void __launch_bounds__(256) kb_blend_kernel(const void* __restrict__ x, const float* __restrict__ mask,
+                                                       float* __restrict__ out, int B, int C, int H, int W,
+                                                       unsigned chan_mask) {
+  const size_t n = size_t(B) * C * H * W;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+    const int xx = int(i % W), yy = int((i / W) % H);
+    const int c = int((i / (size_t(W) * H)) % C), b = int(i / (size_t(W) * H * C));
+    const size_t plane = i - size_t(yy) * W - xx;
+    auto at = [&](int y, int x_) {
+      y = y < 0 ? -y : (y >= H ? 2 * H - 2 - y : y);       // reflect (padding_mode of F.pad(..., mode='reflect'))
+      x_ = x_ < 0 ? -x_ : (x_ >= W ? 2 * W - 2 - x_ : x_);
+      const size_t o = plane + size_t(y) * W + x_;
+      if constexpr (kFloatIn) return static_cast<const float*>(x)[o];
+      else return __fdiv_rn(float(static_cast<const uint8_t*>(x)[o]), 255.f);
+    };
+    const float v = at(yy, xx);
+    if (!((chan_mask >> c) & 1u)) { out[i] = v; continue; }
+    const float cross = (at(yy - 1, xx) + at(yy + 1, xx)) + (at(yy, xx - 1) + at(yy, xx + 1));
+    const float diag = (at(yy - 1, xx - 1) + at(yy - 1, xx + 1)) + (at(yy + 1, xx - 1) + at(yy + 1, xx + 1));
+    const float kb = 0.5f * cross - 0.25f * diag;
+    const float m = mask[(size_t(b) * H + yy) * W + xx];
+    out[i] = v * m + kb * (1.f - m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ matrix-form residuals
+// src/filters/evaluate.py:53-76 get_filter_residuals: rows of the N x 9 neighbour matrix (src/_defs/filters.py:39-69; columns
+// x00 x01 x02 x12 x22 x21 x20 x10 | x11) against an 8 x 1 float64 filter: resid = x11 - sum_k coef[k] * row[k], in float64.
+template <typename T>
+__global__ void __launch_bounds__(256) residual_matvec_kernel(const T* __restrict__ mat, const double* __restrict__ coef,
+                                                              double* __restrict__ resid, long long n) {
+  double k[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) k[j] = coef[j];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const T* r = mat + i * 9;
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += double(r[j]) * k[j];     // same left-to-right order as a row-times-column product
+    resid[i] = double(r[8]) - acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ debug pack/unpack
 __global__ void pack_kernel(const float* __restrict__ src, Act dst) {
   const size_t n = size_t(dst.B) * dst.C * dst.H * dst.W;
@@ -1150,6 +1199,24 @@ cudaError_t launch_finalize(const float* partials, int records, int B, float npi
   const int warps_per_block = 4;
   finalize_kernel<<<(B + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
       partials, records, B, npix, clip, correct_bias, beta_hat, l1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kb_blend(const void* x, int x_is_float, const float* mask, float* out, int B, int C, int H, int W,
+                            unsigned chan_mask, cudaStream_t stream) {
+  const size_t n = size_t(B) * C * H * W;
+  const int grid = int(std::min<size_t>((n + 255) / 256, 148 * 16));
+  if (x_is_float) kb_blend_kernel<true><<<grid, 256, 0, stream>>>(x, mask, out, B, C, H, W, chan_mask);
+  else kb_blend_kernel<false><<<grid, 256, 0, stream>>>(x, mask, out, B, C, H, W, chan_mask);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_residual_matvec(const void* mat, int mat_dtype, const double* coef, double* resid, long long n,
+                                   cudaStream_t stream) {
+  const int grid = int(std::min<long long>((n + 255) / 256, 148 * 16));
+  if (mat_dtype == 0) residual_matvec_kernel<uint8_t><<<grid, 256, 0, stream>>>(static_cast<const uint8_t*>(mat), coef, resid, n);
+  else if (mat_dtype == 1) residual_matvec_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(mat), coef, resid, n);
+  else residual_matvec_kernel<double><<<grid, 256, 0, stream>>>(static_cast<const double*>(mat), coef, resid, n);
   return cudaGetLastError();
 }
 

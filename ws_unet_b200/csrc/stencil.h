@@ -35,6 +35,11 @@ cudaError_t launch_ws_grad_pred(const void* img, int img_is_float, const float* 
                                 int crop, float scale, cudaStream_t stream);
 cudaError_t launch_finalize(const float* partials, int records, int B, float npix, int clip, int correct_bias,
                             float* beta_hat, float* l1, cudaStream_t stream);
+cudaError_t launch_kb_blend(const void* x, int x_is_float, const float* mask, float* out, int B, int C, int H, int W,
+                            unsigned chan_mask, cudaStream_t stream);
+// mat_dtype: 0 uint8, 1 float32, 2 float64
+cudaError_t launch_residual_matvec(const void* mat, int mat_dtype, const double* coef, double* resid, long long n,
+                                   cudaStream_t stream);
 cudaError_t launch_pack(const float* src, Act dst, cudaStream_t stream);
 cudaError_t launch_unpack(Act src, float* dst, int with_halo, cudaStream_t stream);
 

@@ -75,16 +75,27 @@ def get_filter_residuals(fname: str, filter: np.ndarray, process_image: typing.C
                          device=None, **kw) -> np.ndarray:
     """src/filters/evaluate.py:53-76: residual of the linear predictor `filter` (8 x 1, float64) over the neighbour
     matrix `process_image(imread(fname))` (N x 9, last column = target) -> (N, 1) float64. Any coefficient vector is
-    allowed (this is the OLS-fit path, not the per-image hot path): one float64 matrix-vector product on the GPU.
-    For the named KB / AVG vectors on 8-bit pixels every term is a multiple of 1/8 below 2^11, so the float64 result
-    is exact and equals `filter_residuals(image, name)` (the stencil kernel) element for element."""
+    allowed (this is the OLS-fit path, not the per-image hot path): `wsu_filter_residual_rows` accumulates each row in
+    float64 in the reference's column order. For the named KB / AVG vectors on 8-bit pixels every term is a multiple of
+    1/8 below 2^11, so the result is exact and equals `filter_residuals(image, name)` (the stencil kernel)."""
     from . import defs
     dev = _device(device)
-    mat = np.asarray(process_image((imread or defs.imread4_u8)(fname)))
-    xt = torch.from_numpy(np.ascontiguousarray(mat[..., :-1], dtype=np.float64)).to(dev)
-    yt = torch.from_numpy(np.ascontiguousarray(mat[..., -1:], dtype=np.float64)).to(dev)
-    coef = torch.from_numpy(np.ascontiguousarray(filter, dtype=np.float64)).to(dev)
-    return (yt - xt @ coef).cpu().numpy()
+    mat = np.ascontiguousarray(np.asarray(process_image((imread or defs.imread4_u8)(fname))))
+    if mat.ndim != 2 or mat.shape[1] != 9:
+        raise ValueError(f'expected an N x 9 neighbour matrix, got {mat.shape}')
+    code = {np.dtype('uint8'): 0, np.dtype('float32'): 1, np.dtype('float64'): 2}.get(mat.dtype)
+    if code is None:
+        mat, code = mat.astype(np.float64), 2
+    mt = torch.from_numpy(mat).to(dev)
+    coef = torch.from_numpy(np.ascontiguousarray(np.asarray(filter, dtype=np.float64).reshape(-1))).to(dev)
+    if coef.numel() != 8:
+        raise ValueError('filter must hold 8 coefficients (src/filters/evaluate.py:22-27)')
+    out = torch.empty(mat.shape[0], dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _native.check(_native.load().wsu_filter_residual_rows(
+            dev.index, ctypes.c_void_p(mt.data_ptr()), code, ctypes.c_void_p(coef.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+            mat.shape[0], _native.stream_ptr(dev)), 'wsu_filter_residual_rows')
+    return out.cpu().numpy()[:, None]
 
 
 def infere_single(x: np.ndarray, filter_name: str, device=None) -> np.ndarray:

@@ -24,8 +24,8 @@ class UniformDropout(nn.Module):
     """Input dropout of the reference (unet.py:15-51): every pixel is kept with probability 1-drop_rate and otherwise
     replaced by its KB prediction (reflect padding). With drop_rate=0 (every shipped inference path,
     src/unet/evaluate.py:175-181) the keep-probability is 1 and the layer is the identity, so it is elided.
-    For drop_rate>0 (training-time feature) the blend runs as plain torch ops on the input's
-    device. Differences from the reference, both deliberate: the caller's tensor is NOT modified in place, and the mask
+    For drop_rate>0 (training-time feature) the KB prediction and the blend run in libwsunet
+    (`wsu_uniform_dropout`). Differences from the reference, both deliberate: the caller's tensor is NOT modified in place, and the mask
     comes from the device RNG (the reference draws it on the CPU), so masks are not reproducible across the two."""
 
     def __init__(self, p: float, drop_channel):
@@ -38,13 +38,22 @@ class UniformDropout(nn.Module):
     def forward(self, x):
         if self.p == 1:
             return x
-        c = list(self.drop_channel)
-        xf = x.to(torch.float32) / 255. if x.dtype == torch.uint8 else x
-        self.mask = torch.empty(xf.shape[0], 1, *xf.shape[2:], device=xf.device).bernoulli_(p=self.p).repeat(1, len(c), 1, 1)
-        x_pad = torch.nn.functional.pad(xf[:, c], (1, 1, 1, 1), mode='reflect')
-        x_kb = torch.nn.functional.conv2d(x_pad, self.kb.to(xf.device).repeat(len(c), 1, 1, 1), groups=len(c))
-        out = xf.clone()
-        out[:, c] = xf[:, c] * self.mask + x_kb * (1 - self.mask)
+        if not x.is_cuda:
+            raise RuntimeError("ws_unet_b200 runs on a CUDA device only (no CPU fallback)")
+        c = [int(v) for v in self.drop_channel]
+        x = x.contiguous() if x.dtype == torch.uint8 else x.to(torch.float32).contiguous()
+        B, C, H, W = x.shape
+        # the keep-mask is drawn by torch's device RNG; the KB prediction and the blend run in libwsunet (wsu_uniform_dropout)
+        self.mask = torch.empty(B, 1, H, W, device=x.device).bernoulli_(p=self.p)
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+        bits = 0
+        for ch in c:
+            bits |= 1 << ch
+        with torch.cuda.device(x.device):
+            _native.check(_native.load().wsu_uniform_dropout(
+                x.device.index, ctypes.c_void_p(x.data_ptr()), _native.WSU_U8 if x.dtype == torch.uint8 else _native.WSU_F32,
+                ctypes.c_void_p(self.mask.data_ptr()), ctypes.c_void_p(out.data_ptr()), B, C, H, W, bits,
+                _native.stream_ptr(x.device)), 'wsu_uniform_dropout')
         return out
 
 

@@ -492,6 +492,8 @@ def configure_precision(args, W, lib, h, model, imgs, dev):
     mode = model.active_precision(dev)
     t = {'bf16x3': 3, 'fp16x2': 2, 'fp16x1': 1}[mode]
     terms = {n: (t if n in deep else 3) for n in names}
+    if mode != 'bf16x3':
+        terms['d41'] = 2.5   # its upsampled half (u4, fp16) takes two MMAs per MAC, the skip half (e12) three
     if mode == 'bf16x3':
         arith = 'split-bf16 operands (hi + lo), 3 tcgen05 MMAs per MAC, fp32 accumulation in TMEM; integer WS arithmetic'
         dtype = 'bf16x3'

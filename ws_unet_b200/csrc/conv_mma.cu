@@ -1041,57 +1041,71 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
             // against the fp16 [Whi; Wlo] tile = a single N=128 MMA per K step
             auto issue_block = [&](auto f16_c) {
               constexpr bool F16 = decltype(f16_c)::value;
-              for (int tap = 0; tap < 9; ++tap) {   // tap-major: with 64-cycle MMAs the ring slots turn over in time
-                const int wsl = ws;
-                mbar_wait(&w_full[ws], wph);
-                if (++ws == C::SW) { ws = 0; wph ^= 1; }
-                const uint32_t w_x = smem_u32(sW + wsl * C::W_SLOT), w_y = w_x + 8192;
-                const uint32_t tap_off = uint32_t((tap / 3) * (kHaloTW + 2) + (tap % 3)) * 128;
+              // Three-term layers hold 45 KB boxes in a ring of three (two in use, one prefetched): in tap-major order both
+              // boxes of an item are released at its very end and the second box of the next item / channel block arrives
+              // ~2 500 cycles late (e12: 10.4k cycles per item for 7.8k of MMAs). In groups of three taps, box-major inside
+              // a group, box 0 is released 1/6 item early and box 1 of the successor is first needed one group into it, which
+              // covers the load. Reduced-term layers (22.5 KB boxes, ring of 4 / 6) stay tap-major.
+              constexpr int GT = (TERMS == 3) ? 3 : 1;     // taps per group
+#pragma unroll 1
+              for (int g = 0; g < 9 / GT; ++g) {
+                int wslot[GT];
 #pragma unroll
                 for (int j = 0; j < M_SUB; ++j) {
                   if (j < nslot) {
-                    if (tap == 0) {
-                      mbar_wait(&a_full[as], aph);
-                      a_slot[j] = uint32_t(as);
-                      if (++as == C::SA) { as = 0; aph ^= 1; }
-                    }
-                    tc_fence_after();
-                    const uint64_t ad = make_sw128_desc(smem_u32(sA + a_slot[j] * C::A_BYTES), kHaloSBO);
-                    const uint64_t wxd = make_sw128_desc(w_x), wyd = make_sw128_desc(w_y);
-                    const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                      const uint64_t da_hi = desc_at(desc_lo(ad), desc_hi(ad), tap_off + k * 32);
-                      const uint64_t da_lo = desc_at(desc_lo(ad), desc_hi(ad), tap_off + kHaloRows * 128 + k * 32);
-                      const uint64_t dw_x = desc_at(desc_lo(wxd), desc_hi(wxd), k * 32);
-                      const uint64_t dw_y = desc_at(desc_lo(wyd), desc_hi(wyd), k * 32);
-                      if constexpr (F16) {                 // fp16 A x fp16 [Whi; Wlo]
-                        umma_bf16_2sm(d, da_hi, dw_x, make_idesc_f16_m(256, 128), (c | tap | k) != 0);
-                      } else if constexpr (TERMS == 2) {   // fp16 A x (Whi, Wlo): A read from shared memory once
-                        umma_bf16_2sm_a_fill(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
-                        umma_bf16_2sm_a_lastuse(d, da_hi, dw_y, idesc, 1);
-                      } else if constexpr (TERMS == 1) {   // fp16 A x fp16 W
-                        umma_bf16_2sm(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
-                      } else if constexpr (C::STACKED) {
-                        umma_bf16_2sm(d, da_hi, dw_x, make_idesc_bf16_m(256, 128), (c | tap | k) != 0);  // Ahi * [Whi; Wlo]
-                        umma_bf16_2sm(d, da_lo, dw_y, make_idesc_bf16_m(256, 64), 1);                    // Alo * Whi
-                      } else {
-                        if constexpr (COLL) {   // A_hi read once for its two products (compile-time: a runtime branch in this
-                                                // single-thread issue loop costs ~10 % of the layer)
+                    for (int tt = 0; tt < GT; ++tt) {
+                      const int tap = GT * g + tt;
+                      if (j == 0) {
+                        wslot[tt] = ws;
+                        mbar_wait(&w_full[ws], wph);
+                        if (++ws == C::SW) { ws = 0; wph ^= 1; }
+                      }
+                      const uint32_t w_x = smem_u32(sW + wslot[tt] * C::W_SLOT), w_y = w_x + 8192;
+                      const uint32_t tap_off = uint32_t((tap / 3) * (kHaloTW + 2) + (tap % 3)) * 128;
+                      if (tap == 0) {
+                        mbar_wait(&a_full[as], aph);
+                        a_slot[j] = uint32_t(as);
+                        if (++as == C::SA) { as = 0; aph ^= 1; }
+                      }
+                      tc_fence_after();
+                      const uint64_t ad = make_sw128_desc(smem_u32(sA + a_slot[j] * C::A_BYTES), kHaloSBO);
+                      const uint64_t wxd = make_sw128_desc(w_x), wyd = make_sw128_desc(w_y);
+                      const uint32_t d = tmem_base + uint32_t(acs * kAccCols + j * C::ACC_W);
+#pragma unroll
+                      for (int k = 0; k < 4; ++k) {
+                        const uint64_t da_hi = desc_at(desc_lo(ad), desc_hi(ad), tap_off + k * 32);
+                        const uint64_t da_lo = desc_at(desc_lo(ad), desc_hi(ad), tap_off + kHaloRows * 128 + k * 32);
+                        const uint64_t dw_x = desc_at(desc_lo(wxd), desc_hi(wxd), k * 32);
+                        const uint64_t dw_y = desc_at(desc_lo(wyd), desc_hi(wyd), k * 32);
+                        if constexpr (F16) {                 // fp16 A x fp16 [Whi; Wlo]
+                          umma_bf16_2sm(d, da_hi, dw_x, make_idesc_f16_m(256, 128), (c | tap | k) != 0);
+                        } else if constexpr (TERMS == 2) {   // fp16 A x (Whi, Wlo): A read from shared memory once
                           umma_bf16_2sm_a_fill(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
                           umma_bf16_2sm_a_lastuse(d, da_hi, dw_y, idesc, 1);
-                          umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
-                        } else {
+                        } else if constexpr (TERMS == 1) {   // fp16 A x fp16 W
                           umma_bf16_2sm(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
-                          umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
-                          umma_bf16_2sm(d, da_hi, dw_y, idesc, 1);
+                        } else if constexpr (C::STACKED) {
+                          umma_bf16_2sm(d, da_hi, dw_x, make_idesc_bf16_m(256, 128), (c | tap | k) != 0);  // Ahi * [Whi; Wlo]
+                          umma_bf16_2sm(d, da_lo, dw_y, make_idesc_bf16_m(256, 64), 1);                    // Alo * Whi
+                        } else {
+                          if constexpr (COLL) {   // A_hi read once for its two products (compile-time: a runtime branch in this
+                                                  // single-thread issue loop costs ~10 % of the layer)
+                            umma_bf16_2sm_a_fill(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
+                            umma_bf16_2sm_a_lastuse(d, da_hi, dw_y, idesc, 1);
+                            umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
+                          } else {
+                            umma_bf16_2sm(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
+                            umma_bf16_2sm(d, da_lo, dw_x, idesc, 1);
+                            umma_bf16_2sm(d, da_hi, dw_y, idesc, 1);
+                          }
                         }
                       }
+                      if (j == nslot - 1) umma_commit_2sm(&w_empty[wslot[tt]], 3);
+                      if (tap == 8) umma_commit_2sm(&a_empty[a_slot[j]], 3);
                     }
-                    if (tap == 8) umma_commit_2sm(&a_empty[a_slot[j]], 3);
                   }
                 }
-                umma_commit_2sm(&w_empty[wsl], 3);
               }
             };
             if constexpr (C::STACKED) {

@@ -65,3 +65,30 @@ def test_sharded_nccl_gather_equals_single_gpu():
     for _, got in res:                       # every rank holds the full gathered vector
         for key in single:
             assert np.array_equal(got[key], single[key]), key
+
+
+def test_one_thread_two_devices_host_paths_and_current_device():
+    """One thread driving two GPUs: the host-buffer entry points keep their staging streams per device, every C entry point
+    leaves the caller's current device as it found it, and both devices give the same bits."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip('needs two CUDA devices')
+    import ws_unet_b200 as Wp
+    from oracle import unet_oracle as uo
+    imgs = _images()
+    sd = {k: torch.from_numpy(v) for k, v in uo.numpy_weights(2, seed=9).items()}
+    torch.cuda.set_device(0)
+    res = {}
+    for d in (0, 1, 0, 1):
+        dev = torch.device('cuda', d)
+        m = Wp.get_model('unet_2', 1).to(dev)
+        m.load_state_dict(sd)
+        kb = Wp.ws_estimate_host(imgs, 'KB', weighted=1, device=dev)
+        un = Wp.ws_estimate_host(imgs, m, weighted=0, clip=False, device=dev)
+        dv = Wp.ws_estimate(imgs.to(dev), m, weighted=0, clip=False).cpu()
+        assert torch.cuda.current_device() == 0            # nobody switched the thread's device behind our back
+        assert torch.equal(un, dv)
+        res.setdefault('kb', kb)
+        res.setdefault('un', un)
+        assert torch.equal(kb, res['kb']) and torch.equal(un, res['un'])
+        del m                                               # wsu_destroy on the other device must not switch it either
+        assert torch.cuda.current_device() == 0

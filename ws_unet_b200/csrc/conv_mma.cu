@@ -1204,12 +1204,17 @@ cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream
 // ConvTranspose2d(k=2, s=2) (unet.py:177,183): out[2y+dy][2x+dx][co] = b[co] + sum_ci in[y][x][ci] * w[ci][co][dy][dx].
 // The four phases are stacked along N and the whole (hi, lo) weight set of the CTA's N tile (128 KB) stays in shared
 // memory, so each activation box is read exactly once per N tile and the kernel is bound by its output writes.
-constexpr int kUpThreads = 320;
+constexpr int kUpThreads = 320;          // three-term: warps 0 TMA, 1 MMA, 2..9 epilogue (two groups of four lane quadrants)
+constexpr int kUpThreadsWide = 576;      // one / two terms: 16 epilogue warps (four groups). With a third of the MMAs per box the
+                                         // epilogue (TMEM -> bias -> fp16/split pack -> staged 2x2 pixel-shuffle stores) is what a
+                                         // box waits for: 7 000 cycles of epilogue against 1 000 of MMAs with 8 warps.
 
 // TERMS as in the CTA-pair convolution: 3 = split-bf16 input (hi, lo planes), 2 / 1 = ONE fp16 input plane against fp16
 // (hi, lo) / hi-only weights. The output format (p.out.fmt) is independent of it.
 template <int N_TILE, int TERMS = 3>
-__global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_constant__ UpconvParams p) {
+__global__ void __launch_bounds__(TERMS == 3 ? kUpThreads : kUpThreadsWide, 1) upconv_res_kernel(const __grid_constant__ UpconvParams p) {
+  constexpr int kThreadsUp = TERMS == 3 ? kUpThreads : kUpThreadsWide;
+  constexpr int kEpiGroups = (kThreadsUp / 32 - 2) / 4;        // 2 or 4 groups of four epilogue warps
   constexpr int kBoxBytes = TERMS == 3 ? kABytes : kABytes / 2;  // hi + lo tile (32 KB) or one fp16 tile of 128 pixels x 64 channels
   constexpr int kUpSA = TERMS == 3 ? 2 : 4;
   extern __shared__ uint8_t smem_raw[];
@@ -1217,7 +1222,7 @@ __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_
   uint8_t* sW = smem;                       // cblocks x (hi | lo) x N_TILE rows x 128 B  (<= 128 KB)
   uint8_t* sA = smem + kUpconvResBytes;     // kUpSA x 32 KB
   uint8_t* sScratch = sA + kUpSA * kBoxBytes;
-  float* sBias = reinterpret_cast<float*>(sScratch + kScratchBytes);   // co_t floats
+  float* sBias = reinterpret_cast<float*>(sScratch + (kEpiGroups / 2) * kScratchBytes);   // co_t floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + 256);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + kUpSA;
@@ -1236,12 +1241,12 @@ __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmapA);
     for (int i = 0; i < kUpSA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * kEpiGroups); }
     mbar_init(w_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  for (int i = threadIdx.x; i < p.co_t; i += kUpThreads) sBias[i] = p.bias[nt * p.co_t + i];
+  for (int i = threadIdx.x; i < p.co_t; i += kThreadsUp) sBias[i] = p.bias[nt * p.co_t + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1316,7 +1321,7 @@ __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_
       tc_fence_after();
       const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acs * kAccCols);
 #pragma unroll 1
-      for (int cc = grp * (kChunks / 2); cc < (grp + 1) * (kChunks / 2); ++cc) {
+      for (int cc = grp * (kChunks / kEpiGroups); cc < (grp + 1) * (kChunks / kEpiGroups); ++cc) {
         uint32_t v[32];
         tmem_ld32(tbase + cc * 32, v);
         tmem_ld_wait();
@@ -1358,6 +1363,7 @@ __global__ void __launch_bounds__(kUpThreads, 1) upconv_res_kernel(const __grid_
   }
 }
 constexpr int kUpSmem = kUpconvResBytes + 2 * kABytes + kScratchBytes + 1024 + 256 + 256;
+constexpr int kUpSmemWide = kUpconvResBytes + 2 * kABytes + 2 * kScratchBytes + 1024 + 256 + 256;   // 16 epilogue warps' staging
 
 }  // namespace
 
@@ -1393,13 +1399,13 @@ cudaError_t conv_mma_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upconv_res_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(upconv_res_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
+  e = cudaFuncSetAttribute(upconv_res_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmemWide);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(upconv_res_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
+  e = cudaFuncSetAttribute(upconv_res_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmemWide);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(upconv_res_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
+  e = cudaFuncSetAttribute(upconv_res_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmemWide);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(upconv_res_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
+  e = cudaFuncSetAttribute(upconv_res_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmemWide);
   return e;
 }
 
@@ -1442,11 +1448,11 @@ cudaError_t launch_upconv_res(const UpconvParams& p, int n_tile, int num_sms, cu
     if (n_tile == 256) upconv_res_kernel<256><<<grid, kUpThreads, kUpSmem, stream>>>(p);
     else upconv_res_kernel<128><<<grid, kUpThreads, kUpSmem, stream>>>(p);
   } else if (p.terms == 2) {
-    if (n_tile == 256) upconv_res_kernel<256, 2><<<grid, kUpThreads, kUpSmem, stream>>>(p);
-    else upconv_res_kernel<128, 2><<<grid, kUpThreads, kUpSmem, stream>>>(p);
+    if (n_tile == 256) upconv_res_kernel<256, 2><<<grid, kUpThreadsWide, kUpSmemWide, stream>>>(p);
+    else upconv_res_kernel<128, 2><<<grid, kUpThreadsWide, kUpSmemWide, stream>>>(p);
   } else if (p.terms == 1) {
-    if (n_tile == 256) upconv_res_kernel<256, 1><<<grid, kUpThreads, kUpSmem, stream>>>(p);
-    else upconv_res_kernel<128, 1><<<grid, kUpThreads, kUpSmem, stream>>>(p);
+    if (n_tile == 256) upconv_res_kernel<256, 1><<<grid, kUpThreadsWide, kUpSmemWide, stream>>>(p);
+    else upconv_res_kernel<128, 1><<<grid, kUpThreadsWide, kUpSmemWide, stream>>>(p);
   } else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

@@ -143,3 +143,47 @@ def test_filter_residuals_match_reference_golden(cuda_dev, ws_golden, defs_golde
     got = filters.get_filter_residuals('mem', filter=defs_golden['coef_ols'], imread=lambda f: x4,
                                        process_image=defs.get_processor(channels=(3,), inbayer='01'))
     assert np.abs(got - defs_golden['resid_cover_ols']).max() < 1e-10     # fitted vector: float64 matvec, order of sums differs
+
+
+def test_new_entry_points_reject_bad_arguments(cuda_dev):
+    """wsu_uniform_dropout / wsu_filter_residual_rows / correct_bias: invalid arguments come back as WSU_ERR_INVALID with a
+    message (ValueError in the shim), never as a launch."""
+    import ctypes
+    import ws_unet_b200 as W
+    from ws_unet_b200 import _native
+    lib = _native.load()
+    x = torch.rand(1, 1, 8, 8, device=cuda_dev)
+    m = torch.ones(1, 1, 8, 8, device=cuda_dev)
+    o = torch.empty_like(x)
+    st = _native.stream_ptr(cuda_dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.wsu_uniform_dropout(0, p(x), 1, p(m), p(o), 1, 1, 1, 8, 1, st) == _native.WSU_ERR_INVALID      # H < 2
+    assert lib.wsu_uniform_dropout(0, None, 1, p(m), p(o), 1, 1, 8, 8, 1, st) == _native.WSU_ERR_INVALID
+    assert lib.wsu_uniform_dropout(0, p(x), 7, p(m), p(o), 1, 1, 8, 8, 1, st) == _native.WSU_ERR_INVALID
+    assert lib.wsu_uniform_dropout(0, p(x), 1, p(m), p(o), 1, 1, 8, 8, 0, st) == 0                             # no channel selected: a copy
+    torch.cuda.synchronize()
+    assert torch.equal(o, x)
+    mat = torch.zeros(4, 9, dtype=torch.float64, device=cuda_dev)
+    coef = torch.zeros(8, dtype=torch.float64, device=cuda_dev)
+    out = torch.empty(4, dtype=torch.float64, device=cuda_dev)
+    assert lib.wsu_filter_residual_rows(0, p(mat), 5, p(coef), p(out), 4, st) == _native.WSU_ERR_INVALID
+    assert lib.wsu_filter_residual_rows(0, p(mat), 2, p(coef), p(out), 0, st) == _native.WSU_ERR_INVALID
+    model = W.get_model('unet_1', 1).to(cuda_dev)
+    with pytest.raises(ValueError):
+        W.ws_estimate(torch.rand(1, 1, 16, 16, device=cuda_dev), model, correct_bias=True)     # bias correction needs uint8 pixels
+    with pytest.raises(ValueError):
+        _native.check(lib.wsu_set_option(model.native_handle(cuda_dev), b'precision', 3))
+
+
+def test_filter_residual_rows_float_inputs(cuda_dev):
+    """get_filter_residuals with an arbitrary (OLS-style) coefficient vector on float32 / float64 neighbour matrices."""
+    import ws_unet_b200 as W
+    rng = np.random.default_rng(4)
+    coef = rng.normal(0, 0.3, (8, 1))
+    for dt in (np.float32, np.float64, np.uint8, np.int16):
+        mat = (rng.random((1000, 9)) * 255).astype(dt)
+        got = W.filters.get_filter_residuals('mem', coef, process_image=lambda x: x, imread=lambda f: mat, device=cuda_dev)
+        m64 = mat.astype(np.float64)
+        ref = m64[:, -1:] - m64[:, :-1] @ coef
+        assert got.shape == (1000, 1) and got.dtype == np.float64
+        assert np.abs(got - ref).max() < 1e-10

@@ -360,6 +360,14 @@ def test_kernel_variants_agree(cuda_dev):
         y_fused = m(inp)
         lib.wsu_set_option(h, b'fuse_e11', 0)
         assert torch.equal(y_fused, m(inp))
+    # interior boxes written by TMA tensor stores out of the staging buffer instead of per-lane stores: same bits
+    y_plain = m(xd)
+    lib.wsu_set_option(h, b'tma_store', 1)
+    assert torch.equal(m(xd), y_plain)
+    big = torch.rand(1, 1, 128, 160, device=cuda_dev)
+    y_tma = m(big)
+    lib.wsu_set_option(h, b'tma_store', 0)
+    assert torch.equal(m(big), y_tma)
     with pytest.raises(ValueError):
         _native.check(lib.wsu_set_option(h, b'no_such_option', 1))
 

@@ -139,6 +139,23 @@ int make_w_tmap(CUtensorMap* m, const void* wpack, size_t bytes, int box_rows) {
   return WSU_OK;
 }
 
+// 5-D map for TMA STORES of a 32-pixel x 32-channel chunk: dims as make_act_tmap, box (32 ch, 8 px, 4 rows, 1, 1); the
+// 64-byte inner rows are XOR-swizzled (SWIZZLE_64B) exactly like the epilogue's staging buffer.
+int make_out_tmap(CUtensorMap* m, const Act& a) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(WSU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t Wp = a.W + 2, Hp = a.H + 2;
+  const cuuint32_t planes = a.fmt == ACT_F16 ? 1 : 2;
+  cuuint64_t dims[5] = {cuuint64_t(a.C), Wp, Hp, cuuint64_t(a.B), planes};
+  cuuint64_t strides[4] = {cuuint64_t(a.C) * 2, Wp * a.C * 2, Hp * Wp * a.C * 2, cuuint64_t(a.plane) * 2};
+  cuuint32_t box[5] = {32, 8, 4, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, a.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(WSU_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed with code " + std::to_string(int(r)));
+  return WSU_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- model description
 struct HostTensor {
   std::vector<float> data;
@@ -216,6 +233,10 @@ struct wsu_context {
   // fp16 (hi, lo) / fp16 hi-only weights = 2 / 1 MMAs per MAC and half the activation bytes; the full-resolution layers
   // (e12, d41, d42), whose rounding reaches the output directly, stay three-term. Whether a plan keeps a given model inside
   // the 1e-3 px bar depends on its weights: UNet.calibrate_precision() measures it against plan 0 and picks.
+  int tma_store = 0;          // option "tma_store": interior boxes of the 3x3 halo kernels are written by TMA tensor stores out of
+                              // the staging buffer (one cp.async.bulk.tensor per 32 x 32 chunk and plane instead of 4 LDS + 4 STG per
+                              // lane). Bit-identical, measured neutral (e12 -0.7 %, d41 -1.8 %, e21 / e22 +3-4 %, total +0.4 %): the
+                              // store path costs its bytes, not its instructions. Off by default, kept for A/B runs.
   bool alias_buffers = true;  // option "alias_buffers": feature maps with disjoint lifetimes share arena bytes
   int precision = 0;
   int precision_active = 0;   // what commit could honour (needs resident up-convolutions: unet_1, unet_2)
@@ -358,6 +379,9 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   p.relu = relu;
   p.upsample = upsample;
   if (out) p.out = *out;
+  if (out && !upsample) {
+    if ((rc = make_out_tmap(&p.tmapOut, *out))) return rc;
+  }
   if (pool) { p.do_pool = 1; p.pool = *pool; }
   if (epi == EPI_HEAD) {
     std::memcpy(p.wout, h->wout, sizeof(p.wout));
@@ -553,6 +577,7 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
     p.l2_prefetch = h->l2_prefetch;
     p.a_collector = h->a_collector;
     p.dbg = h->dbg;
+    p.tma_store = (h->tma_store && halo && epi == EPI_ACT && !p.upsample) ? 1 : 0;
     if (nimg != pl.mb) {
       p.B = nimg;
       p.total_tiles = nimg * p.tiles_y * p.tiles_x * p.n_tiles * p.npos;
@@ -763,6 +788,10 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
       h->precision = int(value);
       if (h->committed) return wsu_commit_weights(h);   // weights are packed per plan (bf16 or fp16 pairs); drops the shape plan too
     }
+    return WSU_OK;
+  }
+  if (!std::strcmp(key, "tma_store")) {
+    h->tma_store = value != 0;
     return WSU_OK;
   }
   if (!std::strcmp(key, "alias_buffers")) {

@@ -125,6 +125,7 @@ struct StoreMap {
   size_t off[4];   // element offset of (pixel, channel 0) in a plane; only meaningful where (valid >> i) & 1
   uint32_t valid;
   bool border;
+  bool full;       // every pixel of the warp's 32 lies inside the map (no ragged edge)
 };
 __device__ __forceinline__ StoreMap make_store_map(const Act& o, const BoxGeo& g, int lane, int row0) {
   StoreMap m;
@@ -140,6 +141,7 @@ __device__ __forceinline__ StoreMap make_store_map(const Act& o, const BoxGeo& g
     edge |= ok && (oy == 1 || ox == 1 || oy == o.H - 2 || ox == o.W - 2);
   }
   m.border = __any_sync(0xffffffffu, edge);
+  m.full = __all_sync(0xffffffffu, m.valid == 0xfu);
   return m;
 }
 
@@ -147,14 +149,20 @@ __device__ __forceinline__ StoreMap make_store_map(const Act& o, const BoxGeo& g
 // a 64-byte row per pixel is staged in shared memory and re-read so that 4 consecutive lanes write the 4 consecutive
 // 16-byte pieces of one pixel: a store instruction then touches 8 half-lines instead of 32 different lines
 // (uncoalesced 16-byte stores made the LSU, not the tensor pipe, the limiter of the store-heavy layers).
+// `tm` (may be null): tensor map of the output with box {32 ch, 8 px, 4 rows, 1, 1} and SWIZZLE_64B, which is exactly the
+// staging layout below. Interior boxes of the 8-pixel-wide halo kernels then leave through ONE TMA tensor store per plane,
+// issued by one lane, instead of 4 shared-memory reads + 4 global stores per lane: a third less traffic on the SM's
+// L1 / shared-memory path, which the MMA operand reads of these kernels already saturate.
 __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scratch, int lane, int row0, int c0,
                                                       const uint32_t (&h)[16], const uint32_t (&l)[16], const BoxGeo& g,
-                                                      const StoreMap& map) {
+                                                      const StoreMap& map, const CUtensorMap* tm = nullptr) {
   const int piece = lane & 3;
   const int planes = o.fmt == ACT_SPLIT ? 2 : 1;   // fp16 maps: h holds 32 fp16 channels = the same 64-byte row
+  const bool use_tma = tm != nullptr && !map.border && map.full && g.tw_shift == 3 && !g.up;
 #pragma unroll
   for (int plane = 0; plane < 2; ++plane) {
     if (plane >= planes) break;
+    if (tm != nullptr && lane == 0) tma_store_wait_read();   // a previous TMA store out of this staging buffer has read it
     __syncwarp();
     uint4* mine = reinterpret_cast<uint4*>(scratch + lane * kScratchPitch);
     const int wsw = (lane >> 1) & 3;
@@ -162,6 +170,16 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
     for (int q = 0; q < 4; ++q)
       mine[q ^ wsw] = plane ? make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3])
                             : make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    if (use_tma) {
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        // padded coordinates: pixel (y, x) lives at (y + 1, x + 1); the warp's 32 rows are box rows (row0 >> 3) .. + 3
+        tma_store_5d(tm, scratch, c0, g.x0 + 1, g.y0 + (row0 >> 3) + 1, g.b, plane);
+        tma_store_commit();
+      }
+      continue;
+    }
     __syncwarp();
     __nv_bfloat16* base = o.base + (plane ? o.plane : 0) + c0 + piece * 8;
     if (!map.border) {
@@ -239,7 +257,7 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
 #pragma unroll
         for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
       }
-      if (!(p.dbg & 2)) store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap);
+      if (!(p.dbg & 2)) store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap, p.tma_store ? &p.tmapOut : nullptr);
       if (p.do_pool && !(p.dbg & 1)) {
         // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16). Each exchange moves
         // only the half the partner will keep, so the four lanes of a quad end up with 8 channels each of the pooled
@@ -861,6 +879,7 @@ conv_halo_kernel(const __grid_constant__ ConvParams p) {
       if (lane == 0) mbar_arrive(&acc_empty[acs]);
       if (++acs == 2) { acs = 0; acph ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();   // TMA stores out of this warp's staging buffer are complete before the CTA retires
   }
 
   tc_fence_before();
@@ -1164,6 +1183,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[acs]), 0));
       if (++acs == 2) { acs = 0; acph ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();   // TMA stores out of this warp's staging buffer are complete before the CTA retires
   }
 
   tc_fence_before();

@@ -1180,7 +1180,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty[acs]), 0));
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&acc_empty[acs]), 0));
       if (++acs == 2) { acs = 0; acph ^= 1; }
     }
     if (lane == 0) tma_store_wait_all();   // TMA stores out of this warp's staging buffer are complete before the CTA retires

@@ -200,6 +200,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Remote arrive WITHOUT a memory fence. `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR, which waits until every
+// global store this thread has issued is visible device-wide: an epilogue warp that has just written its box then
+// holds its accumulator stage for the whole drain time of those stores (e12: 13 % of all warp samples sat in that fence).
+// The accumulator handoff orders TMEM reads against the next MMAs, which tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync already do; no global data is published through this barrier.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // 5-D tiled load issued by either CTA of a pair; completion bytes are credited to the mbarrier at `mbar_cluster_addr`
 // (the leader CTA's barrier), data lands in this CTA's shared memory.
 __device__ __forceinline__ void tma_load_5d_2sm(void* dst, const CUtensorMap* m, uint32_t mbar_cluster_addr, int c0, int c1,

@@ -490,13 +490,20 @@ def configure_precision(args, W, lib, h, model, imgs, dev):
         model.set_precision(args.precision)
         report = {'chosen': model.active_precision(dev), 'requested': args.precision}
     mode = model.active_precision(dev)
-    t = {'bf16x3': 3, 'fp16x2': 2, 'fp16x1': 1}[mode]
+    t = {'bf16x3': 3, 'fp16x2': 2, 'fp16x1': 1, 'fp16x1_f8': 1}[mode]
     terms = {n: (t if n in deep else 3) for n in names}
-    if mode != 'bf16x3':
+    if mode in ('fp16x2', 'fp16x1'):
         terms['d41'] = 2.5   # its upsampled half (u4, fp16) takes two MMAs per MAC, the skip half (e12) three
+    if mode == 'fp16x1_f8':  # full-resolution layers: one fp16 MMA + one e4m3 MMA (K = 32 per instruction) per MAC
+        terms.update({'e12': 2, 'd42': 2, 'd41': 1.5})
     if mode == 'bf16x3':
         arith = 'split-bf16 operands (hi + lo), 3 tcgen05 MMAs per MAC, fp32 accumulation in TMEM; integer WS arithmetic'
         dtype = 'bf16x3'
+    elif mode == 'fp16x1_f8':
+        arith = ('full-resolution layers e12/d41/d42: fp16 main product + ONE e4m3 MMA over both correction terms (2 MMA times per MAC, '
+                 '~15 significant bits); layers at level >= 1: one fp16 activation plane x fp16 weights, 1 MMA per MAC (chosen by '
+                 'calibration against the 3-term plan); fp32 accumulation in TMEM; integer WS arithmetic')
+        dtype = 'fp16+e4m3x2 / fp16x1'
     else:
         arith = (f'full-resolution layers e12/d41/d42: split-bf16 operands, 3 tcgen05 MMAs per MAC; layers at level >= 1: one fp16 '
                  f'activation plane x fp16 weights, {t} MMA(s) per MAC ({mode}, chosen by calibration against the 3-term plan); '
@@ -518,7 +525,7 @@ def main():
     ap.add_argument('--est-images', type=int, default=10000, help='images of the KB-filter estimator measurement (configs[1]); 0 skips it (launch lists of the UNet step)')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--size', type=int, default=512, help='image side; 1024 = BASELINE configs[4] (not the headline metric)')
-    ap.add_argument('--precision', default='auto', choices=['auto', 'bf16x3', 'fp16x2', 'fp16x1'])
+    ap.add_argument('--precision', default='auto', choices=['auto', 'bf16x3', 'fp16x2', 'fp16x1', 'fp16x1_f8'])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

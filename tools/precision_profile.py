@@ -23,7 +23,7 @@ def main():
     lib = _native.load()
     model.set_micro_batch(n, dev)
     res, ref = {}, None
-    for mode in ('bf16x3', 'fp16x2', 'fp16x1', 'fp16x1+pair2'):
+    for mode in ('bf16x3', 'fp16x1', 'fp16x1+pair2', 'fp16x1_f8+pair2'):
         model.set_precision(mode.split('+')[0])
         h = model.native_handle(dev)
         lib.wsu_set_option(h, b'cta_pair', 2 if mode.endswith('pair2') else 1)

@@ -2,6 +2,7 @@
 // layer chain of UNet.forward (src/unet/model/unet.py:137-189) and the fused / stand-alone WS estimators.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -87,6 +88,8 @@ float h2f(uint16_t v) {
   r.x = v;
   return __half2float(__half(r));
 }
+// e4m3 on the host (round to nearest even, saturating to +-448), the toolkit's own conversion
+uint8_t f2e4m3(float f) { return uint8_t(__nv_cvt_float_to_fp8(f, __NV_SATFINITE, __NV_E4M3)); }
 inline size_t sw128_off(int row, int k) {  // byte offset of bf16 element (row, k) inside a K-major SWIZZLE_128B tile
   return size_t(row) * 128 + size_t(((k >> 3) ^ (row & 7)) << 4) + size_t(k & 7) * 2;
 }
@@ -169,6 +172,9 @@ struct LayerW {  // device-side packed weights of one tensor-core layer
   int terms = 3;            // MMAs per MAC: 3 = split-bf16 weights against split-bf16 inputs; 2 / 1 = fp16 (hi, lo) / hi weights
                             // against ONE fp16 input plane (precision plan, see wsu_context::precision)
   size_t wpack_bytes = 0;
+  int src0_terms = 2;       // MMAs per MAC of the fp16 source-0 blocks (f16_cblocks0 > 0): 2, or 1 under the fp16 + fp8 plan
+  bool f8 = false;          // the blocks after f16_cblocks0 are ACT_F16F8 maps: fp16 main tile + e4m3 correction tile
+  float corr_scale = 1.f;   // 1 / (kF8ScaleA2 * pw): undoes the scaling of the correction accumulator
   int f16_cblocks0 = 0;     // decoder layer at level 0 under a reduced plan: its first channel blocks (the up-convolution's
                             // output) are fp16 pairs against ONE fp16 plane, the skip half stays three-term
   uint8_t* wres = nullptr;  // transposed conv only: phase-stacked tiles for the resident-weight kernel (may stay null)
@@ -238,6 +244,9 @@ struct wsu_context {
                               // lane). Bit-identical, measured neutral (e12 -0.7 %, d41 -1.8 %, e21 / e22 +3-4 %, total +0.4 %): the
                               // store path costs its bytes, not its instructions. Off by default, kept for A/B runs.
   bool alias_buffers = true;  // option "alias_buffers": feature maps with disjoint lifetimes share arena bytes
+  // 3: plan 2, and the full-resolution 3x3 layers (e12, d41's skip half, d42) read ACT_F16F8 maps: one fp16 MMA for the main
+  // product and ONE e4m3 MMA for both correction terms (two MMA times instead of three at ~15 significant bits - this part
+  // does not depend on the weights, only the deep-layer part of the plan does).
   int precision = 0;
   int precision_active = 0;   // what commit could honour (needs resident up-convolutions: unet_1, unet_2)
   bool use_upres = true;  // transposed convs through upconv_res_kernel (option "upconv_resident")
@@ -358,11 +367,15 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   }
   p.npos = lw.npos;
   p.terms = lw.terms;
-  p.src0_f16 = lw.f16_cblocks0 > 0;
+  p.src0_f16 = lw.f16_cblocks0 > 0 ? (lw.src0_terms == 1 ? 2 : 1) : 0;
+  p.f8_blocks = lw.f8 ? 1 : 0;
+  p.corr_scale = lw.corr_scale;
   {
     const bool in0_f16 = src0.fmt == ACT_F16, in1_f16 = src1 ? src1->fmt == ACT_F16 : in0_f16;
-    const bool ok = p.src0_f16 ? (lw.terms == 3 && in0_f16 && !in1_f16 && lw.f16_cblocks0 == src0.C / 64 && lw.n_tile == 64)
-                               : ((lw.terms != 3) == in0_f16 && in1_f16 == in0_f16);
+    const int rest_fmt = p.src0_f16 ? (src1 ? src1->fmt : -1) : src0.fmt;   // format of the blocks that are not fp16 source-0 blocks
+    bool ok = p.src0_f16 ? (lw.terms == 3 && in0_f16 && !in1_f16 && lw.f16_cblocks0 == src0.C / 64 && lw.n_tile == 64)
+                         : ((lw.terms != 3) == in0_f16 && in1_f16 == in0_f16);
+    ok = ok && (lw.f8 ? (rest_fmt == ACT_F16F8 && lw.n_tile == 64) : rest_fmt != ACT_F16F8);
     if (!ok) return fail(WSU_ERR_STATE, "internal: layer " + lname + " and its input maps disagree about the precision plan");
   }
   p.n_tiles = lw.cout / lw.n_tile;
@@ -437,7 +450,10 @@ void describe_chain(const wsu_context* h, int mb, int H, int W, std::vector<ActD
   // activations. Under a reduced-precision plan every map at level >= 1 (and every up-convolution output) is read only by
   // one-/two-term layers or channel blocks and is stored as ONE fp16 plane; e11, e12, d41 feed three-term layers and stay
   // split-bf16.
-  auto fmt_at = [&](int level) { return (h->precision_active != 0 && level >= 1) ? int(ACT_F16) : int(ACT_SPLIT); };
+  auto fmt_at = [&](int level) {
+    if (h->precision_active != 0 && level >= 1) return int(ACT_F16);
+    return h->precision_active == 3 ? int(ACT_F16F8) : int(ACT_SPLIT);   // level-0 maps read by the full-resolution 3x3 layers
+  };
   for (int l = 0; l <= n; ++l) {
     const int hh = H >> l, ww = W >> l;
     declare_act(decls, enc_name(l, 1), mb, hh, ww, chan(l), fmt_at(l));
@@ -565,11 +581,11 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
     const ConvParams& c0 = pl.convs[0].first;
     const int nt0 = pl.convs[0].second.first, epi0 = pl.convs[0].second.second;
     fuse_first = h->fuse_e11 && h->use_halo && h->in_ch == 1 && epi0 == EPI_ACT && nt0 == 64 &&
-                 c0.cblocks == 1 && c0.ntaps == 9 && !bias_pass;
+                 c0.cblocks == 1 && c0.ntaps == 9 && !bias_pass && !c0.f8_blocks;
   }
   if (!fuse_first)
     LAUNCH_TRY(launch_first_conv(img, bias_pass ? 2 : (img_dtype == WSU_F32 ? 1 : 0), h->in_ch, h->e11_w, h->e11_b,
-                                 Act{first.base, first.plane, nimg, first.H, first.W, first.C}, st));
+                                 Act{first.base, first.plane, nimg, first.H, first.W, first.C, first.fmt}, st));
   for (size_t i = 0; i < pl.convs.size(); ++i) {
     ConvParams p = pl.convs[i].first;
     const int n_tile = pl.convs[i].second.first, epi = pl.convs[i].second.second;
@@ -602,6 +618,9 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
     mark(i + 1);
     if (i == 0 && fuse_first) {
       LAUNCH_TRY(launch_conv_halo(p, n_tile, epi, h->num_sms, st));   // e11 computed by e12's producer warps (single-CTA kernel)
+    } else if (p.f8_blocks || p.src0_f16 == 2) {   // fp16 + fp8 blocks / one-term source-0 blocks exist in the CTA-pair kernel only
+      p.total_items = ((p.total_sub + 3) / 4) * p.n_tiles;
+      LAUNCH_TRY(launch_conv_halo2(p, n_tile, epi, h->num_sms, st));
     } else if (p.src0_f16) {
       if (h->use_pair == 2) {
         p.total_items = ((p.total_sub + 3) / 4) * p.n_tiles;
@@ -724,7 +743,7 @@ int wsu_create(wsu_handle* out, int device, int nsteps, int in_channels, int out
   if (const char* e = std::getenv("WSU_HALO")) h->use_halo = std::atoi(e) != 0;
   if (const char* e = std::getenv("WSU_A_COLLECTOR")) h->a_collector = std::atoi(e) != 0;
   if (const char* e = std::getenv("WSU_DBG")) h->dbg = std::atoi(e);
-  if (const char* e = std::getenv("WSU_PRECISION")) h->precision = std::max(0, std::min(2, std::atoi(e)));
+  if (const char* e = std::getenv("WSU_PRECISION")) h->precision = std::max(0, std::min(3, std::atoi(e)));
   *out = h;
   return WSU_OK;
 }
@@ -783,7 +802,8 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
     return WSU_OK;
   }
   if (!std::strcmp(key, "precision")) {
-    if (value < 0 || value > 2) return fail(WSU_ERR_INVALID, "precision must be 0 (three-term), 1 (two-term deep layers) or 2 (one-term deep layers)");
+    if (value < 0 || value > 3)
+      return fail(WSU_ERR_INVALID, "precision must be 0 (three-term), 1 / 2 (two- / one-term deep layers) or 3 (2 + fp16/fp8 full-resolution layers)");
     if (h->precision != int(value)) {
       h->precision = int(value);
       if (h->committed) return wsu_commit_weights(h);   // weights are packed per plan (bf16 or fp16 pairs); drops the shape plan too
@@ -840,7 +860,8 @@ static int expect_dims(wsu_context* h, const std::string& name, std::vector<int6
 // f16_cblocks0: leading 64-channel blocks packed as fp16 pairs although the layer is three-term (decoder source 0);
 // bias_override: bias to upload instead of the state_dict's (up-convolution bias folded away / folded in)
 static int upload_layer(wsu_context* h, const std::string& name, int cin, int cout, bool transposed, int terms,
-                        int f16_cblocks0 = 0, const std::vector<float>* bias_override = nullptr) {
+                        int f16_cblocks0 = 0, const std::vector<float>* bias_override = nullptr, bool f8 = false,
+                        int src0_terms = 2) {
   const HostTensor *w, *b;
   int rc;
   if (transposed) {
@@ -853,6 +874,20 @@ static int upload_layer(wsu_context* h, const std::string& name, int cin, int co
   lw.cin = cin; lw.cout = cout;
   lw.terms = terms;
   lw.f16_cblocks0 = f16_cblocks0;
+  lw.f8 = f8;
+  lw.src0_terms = src0_terms;
+  // fp16 + fp8 blocks: power-of-two scales. w * pw fills e4m3's range; (w - fp16(w)) * sw with sw = A2 * pw / A1 makes both
+  // correction products carry the same total scale A2 * pw, which corr_scale removes in the epilogue.
+  float pw = 1.f, sw = 1.f;
+  if (f8) {
+    float wmax = 0.f;
+    for (int co = 0; co < cout; ++co)
+      for (int ci = f16_cblocks0 * 64; ci < cin; ++ci)
+        for (int t = 0; t < 9; ++t) wmax = std::max(wmax, std::fabs(w->data[(size_t(co) * cin + ci) * 9 + t]));
+    if (wmax > 0.f) pw = std::exp2(std::floor(std::log2(256.f / wmax)));
+    sw = kF8ScaleA2 * pw / kF8ScaleA1;
+    lw.corr_scale = 1.f / (kF8ScaleA2 * pw);
+  }
   // (hi, lo) pair of one weight in its channel block's operand type: bf16 for the three-term scheme, fp16 under a reduced plan
   auto split16 = [terms, f16_cblocks0](float v, int cblock, uint16_t& vh, uint16_t& vl) {
     if (terms == 3 && cblock >= f16_cblocks0) { vh = f2bf(v); vl = f2bf(v - bf2f(vh)); }
@@ -878,6 +913,17 @@ static int upload_layer(wsu_context* h, const std::string& name, int cin, int co
                 v = w->data[((size_t(ci) * cout + co) * 2 + (pos >> 1)) * 2 + (pos & 1)];
               else
                 v = w->data[((size_t(co) * cin + ci) * 3 + tap / 3) * 3 + tap % 3];
+              if (f8 && c >= f16_cblocks0) {
+                // main tile: fp16(w); correction tile: per 16-channel group the 32 bytes [e4m3(w pw) x16 | e4m3((w - fp16 w) sw) x16]
+                const uint16_t vm = f2h(v);
+                std::memcpy(hi + sw128_off(n, k), &vm, 2);
+                const int g = k >> 4, i = k & 15;
+                uint8_t* row = lo + size_t(n) * 128;
+                auto byte_at = [&](int b) -> uint8_t& { return row[size_t((((b >> 4) ^ (n & 7)) << 4) + (b & 15))]; };   // SWIZZLE_128B on bytes
+                byte_at(32 * g + i) = f2e4m3(v * pw);
+                byte_at(32 * g + 16 + i) = f2e4m3((v - h2f(vm)) * sw);
+                continue;
+              }
               uint16_t vh, vl;
               split16(v, c, vh, vl);
               std::memcpy(hi + sw128_off(n, k), &vh, 2);
@@ -949,11 +995,13 @@ int wsu_commit_weights(wsu_handle h) {
     if (!fits) h->precision_active = 0;
   }
   if (n == 0) h->precision_active = 0;
-  const int deep_terms = h->precision_active == 2 ? 1 : h->precision_active == 1 ? 2 : 3;
+  if (h->precision_active == 3 && h->in_ch != 1) h->precision_active = 2;   // the ACT_F16F8 first layer exists for one input channel
+  const bool f8 = h->precision_active == 3;
+  const int deep_terms = h->precision_active >= 2 ? 1 : h->precision_active == 1 ? 2 : 3;
   auto terms_at = [&](int input_level) { return input_level >= 1 ? deep_terms : 3; };
   for (int l = 0; l <= n; ++l) {
     if (l > 0 && (rc = upload_layer(h, enc_name(l, 1), chan(l - 1), chan(l), false, terms_at(l)))) return rc;
-    if ((rc = upload_layer(h, enc_name(l, 2), chan(l), chan(l), false, terms_at(l)))) return rc;
+    if ((rc = upload_layer(h, enc_name(l, 2), chan(l), chan(l), false, terms_at(l), 0, nullptr, f8 && l == 0))) return rc;
   }
   for (int l = n - 1; l >= 0; --l) {
     if (!h->precision_active) {
@@ -981,10 +1029,10 @@ int wsu_commit_weights(wsu_handle h) {
       }
       if ((rc = upload_layer(h, up_name(l), chan(l + 1), chan(l), true, deep_terms, 0, &zero))) return rc;
       if (l >= 1) rc = upload_layer(h, dec_name(l, 1), 2 * chan(l), chan(l), false, deep_terms, 0, &folded);
-      else rc = upload_layer(h, dec_name(l, 1), 2 * chan(l), chan(l), false, 3, cu / 64, &folded);
+      else rc = upload_layer(h, dec_name(l, 1), 2 * chan(l), chan(l), false, 3, cu / 64, &folded, f8, f8 ? 1 : 2);
       if (rc) return rc;
     }
-    if ((rc = upload_layer(h, dec_name(l, 2), chan(l), chan(l), false, terms_at(l)))) return rc;
+    if ((rc = upload_layer(h, dec_name(l, 2), chan(l), chan(l), false, terms_at(l), 0, nullptr, f8 && l == 0))) return rc;
   }
   if ((rc = expect_dims(h, "outconv.weight", {1, 64, 1, 1}, &w))) return rc;
   if ((rc = expect_dims(h, "outconv.bias", {1}, &b))) return rc;

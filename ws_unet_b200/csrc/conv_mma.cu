@@ -88,7 +88,7 @@ __device__ __forceinline__ void store_pixel8(const Act& o, int b, int oy, int ox
                                              const uint32_t (&l)[4]) {
   const uint4 vh = make_uint4(h[0], h[1], h[2], h[3]), vl = make_uint4(l[0], l[1], l[2], l[3]);
   const size_t off = ((size_t(b) * (o.H + 2) + (oy + 1)) * (o.W + 2) + (ox + 1)) * o.C + c0;
-  const bool two = o.fmt == ACT_SPLIT;   // fp16 maps have one plane (h holds the fp16 words)
+  const bool two = o.fmt != ACT_F16;   // fp16 maps have one plane (h holds the fp16 words)
   *reinterpret_cast<uint4*>(o.base + off) = vh;
   if (two) *reinterpret_cast<uint4*>(o.base + o.plane + off) = vl;
   if (oy == 1 || ox == 1 || oy == o.H - 2 || ox == o.W - 2) {   // reflect-halo duplicates (border pixels only)
@@ -157,7 +157,7 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
                                                       const uint32_t (&h)[16], const uint32_t (&l)[16], const BoxGeo& g,
                                                       const StoreMap& map, const CUtensorMap* tm = nullptr) {
   const int piece = lane & 3;
-  const int planes = o.fmt == ACT_SPLIT ? 2 : 1;   // fp16 maps: h holds 32 fp16 channels = the same 64-byte row
+  const int planes = o.fmt == ACT_F16 ? 1 : 2;   // fp16 maps: h holds 32 fp16 channels = the same 64-byte row
   const bool use_tma = tm != nullptr && !map.border && map.full && g.tw_shift == 3 && !g.up;
 #pragma unroll
   for (int plane = 0; plane < 2; ++plane) {
@@ -212,8 +212,9 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
 
 // STACKED (Cout = 64 layers of the halo kernel): the accumulator is 128 columns wide, columns [0,64) hold
 // (Ahi + Alo) * Whi and columns [64,128) hold Ahi * Wlo of the same 64 output channels; they are summed here.
+// Under the fp16 + fp8 scheme the second half holds the correction sum scaled by a power of two (corr_scale undoes it).
 template <int N_TILE, int EPI, bool STACKED>
-__device__ __forceinline__ void load_acc32(uint32_t taddr, float (&f)[32]) {
+__device__ __forceinline__ void load_acc32(uint32_t taddr, float (&f)[32], float corr_scale) {
   uint32_t v[32];
   tmem_ld32(taddr, v);
   if constexpr (STACKED) {
@@ -221,7 +222,7 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&f)[32]) {
     tmem_ld32(taddr + 64, w);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + __uint_as_float(w[i]);
+    for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(w[i]), corr_scale, __uint_as_float(v[i]));
   } else {
     tmem_ld_wait();
 #pragma unroll
@@ -239,7 +240,7 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
     for (int cc = 0; cc < N_TILE / 32; ++cc) {
       const int n0 = nt * N_TILE + cc * 32;
       float f[32];
-      load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f);
+      load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f, (p.dbg & 8) ? 0.f : p.corr_scale);   // WSU_DBG=8: correction MMA off (diagnostic)
 #pragma unroll
       for (int i = 0; i < 8; ++i) {   // 128-bit broadcast loads: 8 instead of 32 shared-memory wavefronts per chunk
         const float4 bq = *reinterpret_cast<const float4*>(sBias + n0 + 4 * i);
@@ -253,6 +254,8 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
       if (p.out.fmt == ACT_F16) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) { h[i] = cvt_f16x2(f[2 * i], f[2 * i + 1]); l[i] = 0u; }
+      } else if (p.out.fmt == ACT_F16F8) {
+        pack_f16f8_32(f, h, l);
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
@@ -293,7 +296,7 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
 #pragma unroll 1
     for (int cc = 0; cc < N_TILE / 32; ++cc) {
       float f[32];
-      load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f);
+      load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f, p.corr_scale);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 bq = *reinterpret_cast<const float4*>(sBias + cc * 32 + 4 * i);
@@ -932,6 +935,16 @@ struct H2Cfg {
   static constexpr int SMEM = SA * A_BYTES + SW * W_SLOT + kScratchBytes + 1024 + BIAS_BYTES + 512 /*barriers*/;
 };
 
+// How one 64-channel block of a stacked (Cout = 64) layer is multiplied. SPLIT3: split-bf16 planes, hi*[Whi;Wlo] (N=128) +
+// lo*Whi (N=64). F16_2 / F16_1: ONE fp16 plane (source 0 of a decoder layer under a reduced plan) against fp16 [Whi;Wlo]
+// (N=128) / Whi (N=64). F8: ACT_F16F8 planes - fp16 main product (N=64, columns [0,64)) + ONE e4m3 MMA over the two
+// correction operands (N=64, columns [64,128), scaled; the epilogue multiplies by ConvParams::corr_scale).
+enum : int { MODE_SPLIT3 = 0, MODE_F16_2 = 1, MODE_F16_1 = 2, MODE_F8 = 3 };
+__device__ __forceinline__ int block_mode(const ConvParams& p, int c) {
+  if (p.src0_f16 && c < p.cblocks0) return p.src0_f16 == 2 ? MODE_F16_1 : MODE_F16_2;
+  return p.f8_blocks ? MODE_F8 : MODE_SPLIT3;
+}
+
 template <int N_TILE, int EPI, bool COLL = true, int TERMS = 3>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __grid_constant__ ConvParams p) {
   static_assert(TERMS == 3 || N_TILE == 128, "the one- and two-term variants exist for the Cout >= 128 layers only");
@@ -1027,10 +1040,21 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
           // the packed weights seen as rows of 128 B: 64- (or 32-) row boxes, raw copy (they are stored pre-swizzled)
           if constexpr (C::STACKED) {
             const uint32_t full_leader = mapa_u32(smem_u32(&w_full[ws]), 0);
-            const int row0 = (nt * chunks + q) * 2 * N_TILE;                        // chunk = [Whi 64 rows][Wlo 64 rows]
-            if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * C::W_BYTES);
-            tma_load_2d_2sm(dst, &p.tmapW, full_leader, 0, row0 + int(rank) * 64);           // X: rank 0 Whi, rank 1 Wlo: [Whi; Wlo] over the pair
-            tma_load_2d_2sm(dst + 8192, &p.tmapW32, full_leader, 0, row0 + int(rank) * 32);  // Y: this CTA's half of Whi
+            const int row0 = (nt * chunks + q) * 2 * N_TILE;                        // chunk = two 64-row tiles of 8 KB
+            const int mode = block_mode(p, q / 9);
+            if (mode == MODE_F8) {
+              // [main fp16 tile][correction e4m3 tile]: this CTA's 32 rows of each (the pair's B operand has N = 64)
+              if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * 8192);
+              tma_load_2d_2sm(dst, &p.tmapW32, full_leader, 0, row0 + int(rank) * 32);
+              tma_load_2d_2sm(dst + 8192, &p.tmapW32, full_leader, 0, row0 + 64 + int(rank) * 32);
+            } else if (mode == MODE_F16_1) {
+              if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * 4096);             // this CTA's 32 rows of the fp16 tile
+              tma_load_2d_2sm(dst, &p.tmapW32, full_leader, 0, row0 + int(rank) * 32);
+            } else {
+              if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * C::W_BYTES);
+              tma_load_2d_2sm(dst, &p.tmapW, full_leader, 0, row0 + int(rank) * 64);           // X: rank 0 Whi, rank 1 Wlo: [Whi; Wlo] over the pair
+              tma_load_2d_2sm(dst + 8192, &p.tmapW32, full_leader, 0, row0 + int(rank) * 32);  // Y: this CTA's half of Whi
+            }
           } else {
             const uint32_t full_leader = mapa_u32(smem_u32(&w_full[ws]), 0);
             const int row_hi = (nt * chunks + q) * 2 * N_TILE + int(rank) * 64;
@@ -1047,6 +1071,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
       if (leader) {
         // ===================================================== leader: MMA issuer for the pair
         constexpr uint32_t idesc = TERMS == 3 ? make_idesc_bf16_m(256, N_TILE) : make_idesc_f16_m(256, N_TILE);
+        const int f8_first = p.src0_f16 ? p.cblocks0 : 0;   // first channel block that accumulates into the correction columns
         int as = 0, ws = 0, acs = 0;
         uint32_t aph = 0, wph = 0, acph = 0;
         for (int item = pair; item < items; item += npairs) {
@@ -1058,8 +1083,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
             uint32_t a_slot[M_SUB];
             // F16 blocks (stacked Cout = 64 kernel only): source 0 of a decoder layer under a reduced plan, one fp16 plane
             // against the fp16 [Whi; Wlo] tile = a single N=128 MMA per K step
-            auto issue_block = [&](auto f16_c) {
-              constexpr bool F16 = decltype(f16_c)::value;
+            auto issue_block = [&](auto mode_c) {
+              constexpr int MODE = decltype(mode_c)::value;
               // Three-term layers hold 45 KB boxes in a ring of three (two in use, one prefetched): in tap-major order both
               // boxes of an item are released at its very end and the second box of the next item / channel block arrives
               // ~2 500 cycles late (e12: 10.4k cycles per item for 7.8k of MMAs). In groups of three taps, box-major inside
@@ -1097,8 +1122,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
                         const uint64_t da_lo = desc_at(desc_lo(ad), desc_hi(ad), tap_off + kHaloRows * 128 + k * 32);
                         const uint64_t dw_x = desc_at(desc_lo(wxd), desc_hi(wxd), k * 32);
                         const uint64_t dw_y = desc_at(desc_lo(wyd), desc_hi(wyd), k * 32);
-                        if constexpr (F16) {                 // fp16 A x fp16 [Whi; Wlo]
+                        if constexpr (MODE == MODE_F16_2) {         // fp16 A x fp16 [Whi; Wlo]
                           umma_bf16_2sm(d, da_hi, dw_x, make_idesc_f16_m(256, 128), (c | tap | k) != 0);
+                        } else if constexpr (MODE == MODE_F16_1) {  // fp16 A x fp16 Whi
+                          umma_bf16_2sm(d, da_hi, dw_x, make_idesc_f16_m(256, 64), (c | tap | k) != 0);
+                        } else if constexpr (MODE == MODE_F8) {     // fp16 main product, then both corrections in one e4m3 MMA
+                          umma_bf16_2sm(d, da_hi, dw_x, make_idesc_f16_m(256, 64), (c | tap | k) != 0);
+                          if (!(p.dbg & 8)) umma_f8_2sm(d + 64, da_lo, dw_y, make_idesc_f16_m(256, 64), ((c - f8_first) | tap | k) != 0);
                         } else if constexpr (TERMS == 2) {   // fp16 A x (Whi, Wlo): A read from shared memory once
                           umma_bf16_2sm_a_fill(d, da_hi, dw_x, idesc, (c | tap | k) != 0);
                           umma_bf16_2sm_a_lastuse(d, da_hi, dw_y, idesc, 1);
@@ -1128,10 +1158,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
               }
             };
             if constexpr (C::STACKED) {
-              if (p.src0_f16 && c < p.cblocks0) issue_block(std::true_type{});
-              else issue_block(std::false_type{});
+              const int mode = block_mode(p, c);
+              if (mode == MODE_F8) issue_block(std::integral_constant<int, MODE_F8>{});
+              else if (mode == MODE_F16_1) issue_block(std::integral_constant<int, MODE_F16_1>{});
+              else if (mode == MODE_F16_2) issue_block(std::integral_constant<int, MODE_F16_2>{});
+              else issue_block(std::integral_constant<int, MODE_SPLIT3>{});
             } else {
-              issue_block(std::false_type{});
+              issue_block(std::integral_constant<int, MODE_SPLIT3>{});
             }
           }
           umma_commit_2sm(&acc_full[acs], 3);

@@ -43,11 +43,14 @@ struct alignas(64) ConvParams {
   const float* fuse_w;
   const float* fuse_b;
   int l2_prefetch;       // halo kernels: warm L2 with the boxes of the CTA's next work item
-  int dbg;               // timing experiments only (env WSU_DBG): bit 0 skips the pooled output, bit 1 the main output stores
+  int dbg;               // experiments only (env WSU_DBG): bit 0 skips the pooled output, bit 1 the main output stores, bit 3 the e4m3
+                         // correction MMA of the fp16 + fp8 scheme
   int a_collector;       // Cout >= 128 layers: A_hi stays in the tensor core's A collector for its second product
   int terms;             // MMAs per MAC: 3 (split-bf16 inputs) or 2 / 1 (ONE fp16 input plane; CTA-pair kernel, Cout >= 128)
-  int src0_f16;          // Cout = 64 halo kernel: the channel blocks of source 0 are ONE fp16 plane against fp16 (hi, lo) weights
-                         // (two terms, one stacked N=128 MMA per K step); source 1 stays three-term split-bf16
+  int src0_f16;          // Cout = 64 halo kernels: the channel blocks of source 0 are ONE fp16 plane; 1: against fp16 (hi, lo) weights
+                         // (one stacked N=128 MMA per K step), 2: against fp16 weights (one N=64 MMA, CTA-pair kernel only)
+  int f8_blocks;         // Cout = 64 CTA-pair kernel: the remaining blocks are ACT_F16F8 maps (fp16 main + one e4m3 correction MMA)
+  float corr_scale;      // what the correction columns [64,128) of a stacked accumulator are multiplied by (1 for split-bf16)
   // EPI_ACT
   int relu;
   int upsample;          // 1: write phase (pos>>1, pos&1) of a 2x upsampled map (ConvTranspose2d k=2,s=2)

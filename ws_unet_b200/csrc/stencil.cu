@@ -11,6 +11,7 @@
 //   * pack / unpack       - NCHW fp32 <-> split-bf16 NHWC, used by the per-layer parity tests.
 #include <algorithm>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include "stencil.h"
 #include "ws_math.cuh"
 
@@ -88,25 +89,55 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict_
           for (int i = 0; i < 4; ++i) acc[i] = fma2_bcast(v, wr[i][ci * 9 + dy * 3 + dx], acc[i]);
         }
     uint32_t h[4], l[4];
+    if (out.fmt == ACT_F16F8) {
+      // plane 0: 8 fp16 values; plane 1: this thread's 8 channels of the e4m3 correction operands - l[0..1] = a2s bytes,
+      // l[2..3] = a1q bytes; they land 16 bytes apart inside their 16-channel group (see the store below)
+      float v[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float a0, a1;
-      unpack_f32x2(acc[i], a0, a1);
-      split_pack2(fmaxf(a0, 0.f), fmaxf(a1, 0.f), h[i], l[i]);
+      for (int i = 0; i < 4; ++i) {
+        unpack_f32x2(acc[i], v[2 * i], v[2 * i + 1]);
+        v[2 * i] = fmaxf(v[2 * i], 0.f);
+        v[2 * i + 1] = fmaxf(v[2 * i + 1], 0.f);
+        h[i] = cvt_f16x2(v[2 * i], v[2 * i + 1]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&h[2 * i]));
+        const float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&h[2 * i + 1]));
+        l[i] = cvt_e4m3x2((v[4 * i] - a01.x) * kF8ScaleA2, (v[4 * i + 1] - a01.y) * kF8ScaleA2) |
+               (cvt_e4m3x2((v[4 * i + 2] - a23.x) * kF8ScaleA2, (v[4 * i + 3] - a23.y) * kF8ScaleA2) << 16);
+        l[2 + i] = cvt_e4m3x2(v[4 * i] * kF8ScaleA1, v[4 * i + 1] * kF8ScaleA1) |
+                   (cvt_e4m3x2(v[4 * i + 2] * kF8ScaleA1, v[4 * i + 3] * kF8ScaleA1) << 16);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float a0, a1;
+        unpack_f32x2(acc[i], a0, a1);
+        split_pack2(fmaxf(a0, 0.f), fmaxf(a1, 0.f), h[i], l[i]);
+      }
     }
     const uint4 vh = make_uint4(h[0], h[1], h[2], h[3]), vl = make_uint4(l[0], l[1], l[2], l[3]);
-    const size_t off0 = ((size_t(b) * (H + 2) + (y + 1)) * (W + 2) + (x + 1)) * out.C + cg * 8;
-    *reinterpret_cast<uint4*>(out.base + off0) = vh;
-    *reinterpret_cast<uint4*>(out.base + out.plane + off0) = vl;
+    // pix: element offset of (pixel, channel 0) in a plane
+    auto store_planes = [&](size_t pix) {
+      *reinterpret_cast<uint4*>(out.base + pix + cg * 8) = vh;
+      if (out.fmt == ACT_F16F8) {
+        // plane 1 of a pixel = 4 groups of [16 a2s bytes | 16 a1q bytes]; this thread owns 8 channels of group cg / 2
+        uint8_t* p1 = reinterpret_cast<uint8_t*>(out.base + out.plane + pix) + (cg >> 1) * 32 + (cg & 1) * 8;
+        *reinterpret_cast<uint2*>(p1) = make_uint2(vl.x, vl.y);
+        *reinterpret_cast<uint2*>(p1 + 16) = make_uint2(vl.z, vl.w);
+      } else {
+        *reinterpret_cast<uint4*>(out.base + out.plane + pix + cg * 8) = vl;
+      }
+    };
+    store_planes(((size_t(b) * (H + 2) + (y + 1)) * (W + 2) + (x + 1)) * out.C);
     if (y == 1 || x == 1 || y == H - 2 || x == W - 2) {   // reflect-halo duplicates (border pixels only)
       int ys[3], xs[3];
       const int ny = halo_targets(y, H, ys), nx = halo_targets(x, W, xs);
       for (int iy = 0; iy < ny; ++iy)
         for (int ix = 0; ix < nx; ++ix) {
           if (iy == 0 && ix == 0) continue;
-          const size_t off = ((size_t(b) * (H + 2) + ys[iy]) * (W + 2) + xs[ix]) * out.C + cg * 8;
-          *reinterpret_cast<uint4*>(out.base + off) = vh;
-          *reinterpret_cast<uint4*>(out.base + out.plane + off) = vl;
+          store_planes(((size_t(b) * (H + 2) + ys[iy]) * (W + 2) + xs[ix]) * out.C);
         }
     }
   }
@@ -1019,6 +1050,12 @@ __global__ void unpack_kernel(Act src, float* __restrict__ dst, int with_halo) {
     const int sy = with_halo ? y : y + 1, sx = with_halo ? x : x + 1;
     const size_t off = ((size_t(b) * (src.H + 2) + sy) * (src.W + 2) + sx) * src.C + c;
     if (src.fmt == ACT_F16) dst[i] = __half2float(reinterpret_cast<const __half*>(src.base)[off]);
+    else if (src.fmt == ACT_F16F8) {
+      // fp16 value + the stored residual: byte (c % 16) of the a2s run of 16-channel group c / 16 in plane 1
+      const uint8_t* p1 = reinterpret_cast<const uint8_t*>(src.base + src.plane + (off - c));
+      const __nv_fp8_e4m3 r = *reinterpret_cast<const __nv_fp8_e4m3*>(p1 + (c >> 4) * 32 + (c & 15));
+      dst[i] = __half2float(reinterpret_cast<const __half*>(src.base)[off]) + float(r) * (1.f / kF8ScaleA2);
+    }
     else dst[i] = __bfloat162float(src.base[off]) + __bfloat162float(src.base[src.plane + off]);
   }
 }

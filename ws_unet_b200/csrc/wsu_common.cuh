@@ -9,6 +9,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace wsu {
@@ -16,7 +17,15 @@ namespace wsu {
 // Storage formats of a feature map. ACT_SPLIT: two bf16 planes (hi, lo) = 16 significand bits, read by the three-term
 // layers. ACT_F16: ONE fp16 plane (11 significand bits), read by the layers the precision plan runs with one or two MMAs per
 // MAC (api.cu: "precision" option) - half the HBM bytes and half the TMA box.
-enum : int { ACT_SPLIT = 0, ACT_F16 = 1 };
+// ACT_F16F8: plane 0 = fp16(v); plane 1 = the two CORRECTION operands of the "fp16 + fp8" scheme as e4m3 bytes, per 16-channel
+// group g of a 64-channel block the 32 bytes [ e4m3((v - fp16(v)) * kF8ScaleA2) x 16 | e4m3(v * kF8ScaleA1) x 16 ] - one K = 32
+// step of a kind::f8f6f4 MMA against the weight bytes [ e4m3(w * pw) x 16 | e4m3((w - fp16(w)) * sw) x 16 ]:
+//   a*w ~= a1*w1 (fp16 MMA) + [ a2*w1 + a1*w2 ] (ONE fp8 MMA, accumulated apart and scaled back in the epilogue).
+// The correction terms are 2^-11 of the main term, so the 4 significant bits of e4m3 leave ~15 bits overall: the accuracy
+// of the three-term bf16 split at two MMA times instead of three, for any weights. Same bytes per element as ACT_SPLIT.
+enum : int { ACT_SPLIT = 0, ACT_F16 = 1, ACT_F16F8 = 2 };
+constexpr float kF8ScaleA1 = 8.f;        // activations up to 56 stay inside e4m3's range (448); beyond that they saturate
+constexpr float kF8ScaleA2 = 16384.f;    // v - fp16(v) <= 2^-6 for v < 64 -> <= 256
 
 struct Act {
   __nv_bfloat16* base;  // plane 0 (hi, or the fp16 plane); plane 1 (lo) starts at base + plane
@@ -52,6 +61,33 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo_elem, float hi_elem) {
   uint32_t r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
+}
+
+// two floats -> two e4m3 bytes (element 0 in the low byte), round to nearest even, saturating to +-448
+__device__ __forceinline__ uint32_t cvt_e4m3x2(float lo_elem, float hi_elem) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+// 32 channels of one pixel (two 16-channel groups) in the ACT_F16F8 layout: h = 16 fp16x2 words (plane 0), l = the 64 bytes
+// [a2s 0..15 | a1q 0..15 | a2s 16..31 | a1q 16..31] of plane 1
+__device__ __forceinline__ void pack_f16f8_32(const float (&f)[32], uint32_t (&h)[16], uint32_t (&l)[16]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {     // word i of a 16-byte run holds channels 16g + 4i .. 16g + 4i + 3
+      const int c = 16 * g + 4 * i;
+      const uint32_t h0 = cvt_f16x2(f[c], f[c + 1]), h1 = cvt_f16x2(f[c + 2], f[c + 3]);
+      h[8 * g + 2 * i] = h0;
+      h[8 * g + 2 * i + 1] = h1;
+      const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+      const float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+      l[8 * g + i] = cvt_e4m3x2((f[c] - a01.x) * kF8ScaleA2, (f[c + 1] - a01.y) * kF8ScaleA2) |
+                     (cvt_e4m3x2((f[c + 2] - a23.x) * kF8ScaleA2, (f[c + 3] - a23.y) * kF8ScaleA2) << 16);
+      l[8 * g + 4 + i] = cvt_e4m3x2(f[c] * kF8ScaleA1, f[c + 1] * kF8ScaleA1) |
+                         (cvt_e4m3x2(f[c + 2] * kF8ScaleA1, f[c + 3] * kF8ScaleA1) << 16);
+    }
+  }
 }
 
 // Packed fp32 pair arithmetic (Blackwell FFMA2): acc.{lo,hi} = fma.rn(v, w.{lo,hi}, acc.{lo,hi}) - two independent IEEE

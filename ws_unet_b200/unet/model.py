@@ -17,7 +17,7 @@ from torch import nn
 from .. import _native
 
 
-PRECISIONS = {'bf16x3': 0, 'fp16x2': 1, 'fp16x1': 2}   # wsu_set_option(h, "precision", .)
+PRECISIONS = {'bf16x3': 0, 'fp16x2': 1, 'fp16x1': 2, 'fp16x1_f8': 3}   # wsu_set_option(h, "precision", .)
 
 
 class UniformDropout(nn.Module):
@@ -204,7 +204,10 @@ class UNet(nn.Module):
         'bf16x3' (default) - split-bf16 operands, three MMAs per MAC, like the full-resolution layers e12 / d41 / d42;
         'fp16x2' / 'fp16x1' - ONE fp16 activation plane against fp16 (hi, lo) / fp16 weights, two / one MMA per MAC and
         half the activation bytes. Whether a reduced plan keeps the prediction inside the 1e-3 px bar depends on how much
-        of the output the deep path carries for the weights at hand - use `calibrate_precision` to decide."""
+        of the output the deep path carries for the weights at hand - use `calibrate_precision` to decide.
+        'fp16x1_f8' - 'fp16x1', and the full-resolution layers (e12, d41's skip half, d42) compute a*w as one fp16 MMA plus
+        ONE e4m3 MMA over both correction terms ((a - fp16 a) * w and a * (w - fp16 w), 2^-11 of the main term, so fp8's 4
+        bits suffice): two MMA times instead of three at ~15 significant bits, independent of the weights."""
         if mode not in PRECISIONS:
             raise ValueError(f'precision must be one of {list(PRECISIONS)}')
         self._precision = mode
@@ -220,7 +223,8 @@ class UNet(nn.Module):
         return {v: k for k, v in PRECISIONS.items()}[int(out.value)]
 
     @torch.no_grad()
-    def calibrate_precision(self, images: torch.Tensor, budget_px: float = 2e-4, modes=('fp16x1', 'fp16x2')) -> dict:
+    def calibrate_precision(self, images: torch.Tensor, budget_px: float = 2e-4,
+                            modes=('fp16x1_f8', 'fp16x1', 'fp16x2')) -> dict:
         """Pick the cheapest precision plan whose predictions on `images` ((B,C,H,W) uint8 pixels or float32 in [0,1], on the
         device) stay within `budget_px` (max-abs, pixel units) of the three-term plan, which itself sits 2-5e-5 px from the
         FP32 reference. Leaves the chosen plan active and returns {'chosen', 'max_abs_px': {mode: err}, 'budget_px'}."""

@@ -118,14 +118,22 @@ __global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict_
       }
     }
     const uint4 vh = make_uint4(h[0], h[1], h[2], h[3]), vl = make_uint4(l[0], l[1], l[2], l[3]);
+    // ACT_F16F8: a 16-channel group is shared by two neighbouring lanes (even cg: channels 0-7 of the group, odd cg: 8-15). They
+    // swap halves so that the even lane holds the group's 16 a2s bytes and the odd lane its 16 a1q bytes: one 16-byte store each.
+    uint4 v1 = vl;
+    if (out.fmt == ACT_F16F8) {
+      const bool odd = cg & 1;
+      const uint32_t s0 = odd ? vl.x : vl.z, s1 = odd ? vl.y : vl.w;          // odd sends its a2s, even its a1q
+      const unsigned am = __activemask();   // lanes of pixels right of a ragged row segment have left the iteration (both lanes of a pair)
+      const uint32_t r0 = __shfl_xor_sync(am, s0, 1), r1 = __shfl_xor_sync(am, s1, 1);
+      v1 = odd ? make_uint4(r0, r1, vl.z, vl.w) : make_uint4(vl.x, vl.y, r0, r1);
+    }
     // pix: element offset of (pixel, channel 0) in a plane
     auto store_planes = [&](size_t pix) {
       *reinterpret_cast<uint4*>(out.base + pix + cg * 8) = vh;
       if (out.fmt == ACT_F16F8) {
-        // plane 1 of a pixel = 4 groups of [16 a2s bytes | 16 a1q bytes]; this thread owns 8 channels of group cg / 2
-        uint8_t* p1 = reinterpret_cast<uint8_t*>(out.base + out.plane + pix) + (cg >> 1) * 32 + (cg & 1) * 8;
-        *reinterpret_cast<uint2*>(p1) = make_uint2(vl.x, vl.y);
-        *reinterpret_cast<uint2*>(p1 + 16) = make_uint2(vl.z, vl.w);
+        // plane 1 of a pixel = 4 groups of [16 a2s bytes | 16 a1q bytes]: byte offset (cg / 2) * 32 + (cg % 2) * 16 = cg * 16
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out.base + out.plane + pix) + cg * 16) = v1;
       } else {
         *reinterpret_cast<uint4*>(out.base + out.plane + pix + cg * 8) = vl;
       }

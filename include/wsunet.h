@@ -60,7 +60,9 @@ int wsu_commit_weights(wsu_handle h);
  *                         A collector for its second product; 0: every MMA re-reads A from shared memory);
  *          "cta_pair" (default 2: every 3x3 layer runs as CTA pairs, tcgen05 cta_group::2; 1: Cout >= 128 layers only; 0 never);
  *          "precision" (default 0: every layer three-term split-bf16; 1 / 2: the layers whose input lives at UNet level >= 1
- *                       read ONE fp16 activation plane with two / one MMA per MAC - see ws_unet_b200/unet/model.py
+ *                       read ONE fp16 activation plane with two / one MMA per MAC; 3: plan 2 plus the full-resolution layers
+ *                       on an fp16 plane + an e4m3 correction plane, one kind::f16 + one kind::f8f6f4 MMA per MAC, about 15
+ *                       bits per operand for any weights (needs in_channels == 1) - see ws_unet_b200/unet/model.py
  *                       set_precision / calibrate_precision; wsu_get_info "precision" reports what is active);
  *          "upconv_resident" (default 1: transposed convs keep their weights in shared memory; 0: per-phase kernel);
  *          "halo" (default 1: 3x3 layers load one haloed box per channel block; 0: per-tap reload kernel);

@@ -172,7 +172,7 @@ def test_new_entry_points_reject_bad_arguments(cuda_dev):
     with pytest.raises(ValueError):
         W.ws_estimate(torch.rand(1, 1, 16, 16, device=cuda_dev), model, correct_bias=True)     # bias correction needs uint8 pixels
     with pytest.raises(ValueError):
-        _native.check(lib.wsu_set_option(model.native_handle(cuda_dev), b'precision', 3))
+        _native.check(lib.wsu_set_option(model.native_handle(cuda_dev), b'precision', 4))
 
 
 def test_filter_residual_rows_float_inputs(cuda_dev):

@@ -1,6 +1,7 @@
 """Per-layer device times of the UNet chain under each precision plan (CUDA events around every launch, min of `reps`).
 Usage (on a B200): python tools/precision_profile.py [images=32] [reps=3]"""
 import ctypes
+import os
 import sys
 
 import torch
@@ -27,6 +28,10 @@ def main():
         model.set_precision(mode.split('+')[0])
         h = model.native_handle(dev)
         lib.wsu_set_option(h, b'cta_pair', 2 if mode.endswith('pair2') else 1)
+        for kv in os.environ.get('WSU_OPTS', '').split(','):       # e.g. WSU_OPTS=tma_store=1 for A/B runs
+            if '=' in kv:
+                k, v = kv.split('=')
+                _native.check(lib.wsu_set_option(h, k.encode(), int(v)), 'wsu_set_option')
         y = model(imgs[:4])
         if ref is None:
             ref = y

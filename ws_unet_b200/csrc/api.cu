@@ -239,6 +239,7 @@ struct wsu_context {
   // fp16 (hi, lo) / fp16 hi-only weights = 2 / 1 MMAs per MAC and half the activation bytes; the full-resolution layers
   // (e12, d41, d42), whose rounding reaches the output directly, stay three-term. Whether a plan keeps a given model inside
   // the 1e-3 px bar depends on its weights: UNet.calibrate_precision() measures it against plan 0 and picks.
+  int epi_warps = 8;          // option "epi_warps" (8 | 16): epilogue warps per CTA of the CTA-pair 3x3 kernel (activation epilogue)
   int tma_store = 0;          // option "tma_store": interior boxes of the 3x3 halo kernels are written by TMA tensor stores out of
                               // the staging buffer (one cp.async.bulk.tensor per 32 x 32 chunk and plane instead of 4 LDS + 4 STG per
                               // lane). Bit-identical, measured neutral (e12 -0.7 %, d41 -1.8 %, e21 / e22 +3-4 %, total +0.4 %): the
@@ -594,6 +595,7 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
     p.a_collector = h->a_collector;
     p.dbg = h->dbg;
     p.tma_store = (h->tma_store && halo && epi == EPI_ACT && !p.upsample) ? 1 : 0;
+    p.epi_warps = h->epi_warps;
     if (nimg != pl.mb) {
       p.B = nimg;
       p.total_tiles = nimg * p.tiles_y * p.tiles_x * p.n_tiles * p.npos;
@@ -808,6 +810,11 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
       h->precision = int(value);
       if (h->committed) return wsu_commit_weights(h);   // weights are packed per plan (bf16 or fp16 pairs); drops the shape plan too
     }
+    return WSU_OK;
+  }
+  if (!std::strcmp(key, "epi_warps")) {
+    if (value != 8 && value != 16) return fail(WSU_ERR_INVALID, "epi_warps must be 8 or 16");
+    h->epi_warps = int(value);
     return WSU_OK;
   }
   if (!std::strcmp(key, "tma_store")) {

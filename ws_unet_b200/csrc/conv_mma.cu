@@ -155,9 +155,20 @@ __device__ __forceinline__ StoreMap make_store_map(const Act& o, const BoxGeo& g
 // L1 / shared-memory path, which the MMA operand reads of these kernels already saturate.
 __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scratch, int lane, int row0, int c0,
                                                       const uint32_t (&h)[16], const uint32_t (&l)[16], const BoxGeo& g,
-                                                      const StoreMap& map, const CUtensorMap* tm = nullptr) {
+                                                      const StoreMap& map, const CUtensorMap* tm = nullptr, int dbg = 0) {
   const int piece = lane & 3;
   const int planes = o.fmt == ACT_F16 ? 1 : 2;   // fp16 maps: h holds 32 fp16 channels = the same 64-byte row
+  if ((dbg & 32) && !map.border && map.full) {   // WSU_DBG=32 (experiment): every lane stores its own pixel, no staging
+    int oy, ox;
+    g.pixel(row0 + lane, oy, ox);
+    const size_t off = ((size_t(g.b) * (o.H + 2) + (oy + 1)) * (o.W + 2) + (ox + 1)) * o.C + c0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      *reinterpret_cast<uint4*>(o.base + off + q * 8) = make_uint4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+      if (planes == 2) *reinterpret_cast<uint4*>(o.base + o.plane + off + q * 8) = make_uint4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
+    }
+    return;
+  }
   const bool use_tma = tm != nullptr && !map.border && map.full && g.tw_shift == 3 && !g.up;
 #pragma unroll
   for (int plane = 0; plane < 2; ++plane) {
@@ -188,7 +199,7 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
       for (int i = 0; i < 4; ++i) {
         const int q = (lane >> 2) + 8 * i;
         const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * kScratchPitch + ((piece ^ ((q >> 1) & 3)) << 4));
-        if ((map.valid >> i) & 1) *reinterpret_cast<uint4*>(base + map.off[i]) = v;
+        if (((map.valid >> i) & 1) && !(dbg & 16)) *reinterpret_cast<uint4*>(base + map.off[i]) = v;   // WSU_DBG=16: staging without the global stores
       }
     } else {
 #pragma unroll
@@ -204,6 +215,58 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
               const size_t off = ((size_t(g.b) * (o.H + 2) + ys[iy]) * (o.W + 2) + xs[ix]) * o.C;
               *reinterpret_cast<uint4*>(base + off) = v;
             }
+        }
+      }
+    }
+  }
+}
+
+// The same store with HALF the staging bytes (1 KB per warp): the chunk leaves in two 16-channel halves of 32-byte rows; two
+// consecutive lanes write one pixel's 32 bytes = one full sector, a store instruction covers 16 pixels. Used by the kernels
+// with sixteen epilogue warps, whose staging area would not fit next to the operand rings otherwise.
+constexpr int kNarrowPerWarp = 32 * 32;
+__device__ __forceinline__ void store_chunk_narrow(const Act& o, uint8_t* scratch, int lane, int row0, int c0,
+                                                   const uint32_t (&h)[16], const uint32_t (&l)[16], const BoxGeo& g) {
+  const int planes = o.fmt == ACT_F16 ? 1 : 2;
+  const int piece = lane & 1;
+  // both pixels this lane re-reads: q = (lane >> 1) + 16 i
+  size_t off[2];
+  bool ok[2], edge = false;
+  int oy[2], ox[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    ok[i] = g.pixel(row0 + (lane >> 1) + 16 * i, oy[i], ox[i]);
+    off[i] = ((size_t(g.b) * (o.H + 2) + (oy[i] + 1)) * (o.W + 2) + (ox[i] + 1)) * o.C;
+    edge |= ok[i] && (oy[i] == 1 || ox[i] == 1 || oy[i] == o.H - 2 || ox[i] == o.W - 2);
+  }
+  const bool border = __any_sync(0xffffffffu, edge);
+#pragma unroll
+  for (int plane = 0; plane < 2; ++plane) {
+    if (plane >= planes) break;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      __syncwarp();
+      uint4* mine = reinterpret_cast<uint4*>(scratch + lane * 32);
+      const int wsw = (lane >> 2) & 1;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int w0 = 8 * half + 4 * q;
+        mine[q ^ wsw] = plane ? make_uint4(l[w0], l[w0 + 1], l[w0 + 2], l[w0 + 3]) : make_uint4(h[w0], h[w0 + 1], h[w0 + 2], h[w0 + 3]);
+      }
+      __syncwarp();
+      __nv_bfloat16* base = o.base + (plane ? o.plane : 0) + c0 + half * 16 + piece * 8;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int q = (lane >> 1) + 16 * i;
+        const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * 32 + ((piece ^ ((q >> 2) & 1)) << 4));
+        if (!border) {
+          if (ok[i]) *reinterpret_cast<uint4*>(base + off[i]) = v;
+        } else if (ok[i]) {
+          int ys[3], xs[3];
+          const int ny = halo_targets(oy[i], o.H, ys), nx = halo_targets(ox[i], o.W, xs);
+          for (int iy = 0; iy < ny; ++iy)
+            for (int ix = 0; ix < nx; ++ix)
+              *reinterpret_cast<uint4*>(base + ((size_t(g.b) * (o.H + 2) + ys[iy]) * (o.W + 2) + xs[ix]) * o.C) = v;
         }
       }
     }
@@ -230,14 +293,19 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&f)[32], float
   }
 }
 
-template <int N_TILE, int EPI, bool STACKED = false>
+// [cc0, cc1): the 32-channel chunks of the box this warp finishes (all of them with eight epilogue warps; NARROW = the
+// sixteen-warp kernels, where two warps share a box quarter and stage through 1 KB each)
+template <int N_TILE, int EPI, bool STACKED = false, bool NARROW = false>
 __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* sBias, uint32_t tbase, int b, int y, int x,
                                        bool valid, int nt, int pos, int tx, int ty, int pool_xor, WsAcc& acc,
-                                       const BoxGeo& geo, uint8_t* scratch, int lane, int row0) {
+                                       const BoxGeo& geo, uint8_t* scratch, int lane, int row0, int cc0 = 0,
+                                       int cc1 = N_TILE / 32) {
+  if (p.dbg & 4) return;   // WSU_DBG=4: no epilogue work at all (timing experiment: what the MMA pipeline alone takes)
   if constexpr (EPI == EPI_ACT) {
-    const StoreMap smap = make_store_map(p.out, geo, lane, row0);
+    StoreMap smap;
+    if constexpr (!NARROW) smap = make_store_map(p.out, geo, lane, row0);
 #pragma unroll 1
-    for (int cc = 0; cc < N_TILE / 32; ++cc) {
+    for (int cc = cc0; cc < cc1; ++cc) {
       const int n0 = nt * N_TILE + cc * 32;
       float f[32];
       load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f, (p.dbg & 8) ? 0.f : p.corr_scale);   // WSU_DBG=8: correction MMA off (diagnostic)
@@ -260,7 +328,10 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
 #pragma unroll
         for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
       }
-      if (!(p.dbg & 2)) store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap, p.tma_store ? &p.tmapOut : nullptr);
+      if (!(p.dbg & 2)) {
+        if constexpr (NARROW) store_chunk_narrow(p.out, scratch, lane, row0, n0, h, l, geo);
+        else store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap, p.tma_store ? &p.tmapOut : nullptr, p.dbg);
+      }
       if (p.do_pool && !(p.dbg & 1)) {
         // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16). Each exchange moves
         // only the half the partner will keep, so the four lanes of a quad end up with 8 channels each of the pooled
@@ -945,11 +1016,18 @@ __device__ __forceinline__ int block_mode(const ConvParams& p, int c) {
   return p.f8_blocks ? MODE_F8 : MODE_SPLIT3;
 }
 
-template <int N_TILE, int EPI, bool COLL = true, int TERMS = 3>
-__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __grid_constant__ ConvParams p) {
+// EW = epilogue warps per CTA. 8: warp group g finishes box g of the item, every 32-channel chunk. 16: four groups, group g
+// finishes half the chunks of box g & 1 - under the reduced plans an item's MMAs take a third to a half of the three-term time
+// and the epilogue (TMEM read, bias, ReLU, format conversion, staging, stores, pooling) had become the longer leg of the
+// pipeline (WSU_DBG=4 timings: e12 1.32 ms with, 0.92 ms without epilogue work).
+template <int N_TILE, int EPI, bool COLL = true, int TERMS = 3, int EW = 8>
+__global__ void __launch_bounds__((3 + EW) * 32, 1) conv_halo2_kernel(const __grid_constant__ ConvParams p) {
   static_assert(TERMS == 3 || N_TILE == 128, "the one- and two-term variants exist for the Cout >= 128 layers only");
+  static_assert(EW == 8 || (EW == 16 && EPI == EPI_ACT), "sixteen epilogue warps: activation epilogue only");
   using C = H2Cfg<N_TILE, TERMS>;
   constexpr int M_SUB = C::M_SUB;
+  constexpr int kThreadsK = (3 + EW) * 32;
+  constexpr int kWeightWarp = 2 + EW;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -984,11 +1062,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
     // the weight relay it had made every layer with fewer than three MMAs per MAC wait on the relay, not on the tensor pipe.)
     for (int i = 0; i < C::SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::SW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * EW); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
-  for (int i = threadIdx.x; i < p.cout && i < C::BIAS_BYTES / 4; i += kHaloThreads) sBias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.cout && i < C::BIAS_BYTES / 4; i += kThreadsK) sBias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / peer-credited TMA
@@ -1026,7 +1104,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == kWeightWarp) {
     // ===================================================== weight half-tiles of this CTA
     if (elect_one()) {
       int ws = 0;
@@ -1175,7 +1253,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
   } else {
     // ===================================================== epilogue warps (each CTA finishes its own boxes)
     const int quad = warp & 3;
-    const int grp = (warp - 2) >> 2;
+    const int grp = ((warp - 2) >> 2) & 1;          // box slot of the item
+    const int part = (warp - 2) >> 3;               // EW == 16: which half of the box's chunks
+    constexpr int NCH = N_TILE / 32, CPP = NCH / (EW / 8);
     const int row = quad * 32 + lane;
     const int ty = row / kHaloTW, tx = row % kHaloTW;
     int acs = 0;
@@ -1196,8 +1276,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
           const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acs * kAccCols + j * C::ACC_W);
           WsAcc acc;
           const BoxGeo geo{bc.b, bc.y0, bc.x0, 3, p.H, p.W, 0, 0};
-          epilogue_box<N_TILE, EPI, C::STACKED>(p, sBias, tbase, bc.b, y, x, valid, nt, 0, tx, ty, kHaloTW, acc, geo,
-                                                sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32);
+          epilogue_box<N_TILE, EPI, C::STACKED, EW == 16>(p, sBias, tbase, bc.b, y, x, valid, nt, 0, tx, ty, kHaloTW, acc, geo,
+                                                          sScratch + (warp - 2) * (EW == 16 ? kNarrowPerWarp : kScratchPerWarp),
+                                                          lane, quad * 32, part * CPP, (part + 1) * CPP);
           if constexpr (EPI == EPI_HEAD) {
             if (p.partials) {
               const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1), wb = warp_sum(acc.wb);
@@ -1232,9 +1313,10 @@ template <int N_TILE, int EPI>
 cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   int pairs = num_sms / 2;
   if (pairs > p.total_items) pairs = p.total_items;
+  const bool wide = EPI == EPI_ACT && p.epi_warps == 16 && (N_TILE == 64 || p.a_collector);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(kHaloThreads);
+  cfg.blockDim = dim3(wide ? 19 * 32 : kHaloThreads);
   cfg.dynamicSmemBytes = (N_TILE == 128 && p.terms == 2) ? H2Cfg<128, 2>::SMEM : (N_TILE == 128 && p.terms == 1) ? H2Cfg<128, 1>::SMEM : H2Cfg<N_TILE>::SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1244,6 +1326,16 @@ cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if constexpr (EPI == EPI_ACT) {
+    if (wide) {
+      if constexpr (N_TILE == 128) {
+        if (p.terms == 2) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 2, 16>, p);
+        if (p.terms == 1) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 1, 16>, p);
+      }
+      if (p.terms != 3) return cudaErrorInvalidValue;
+      return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<N_TILE, EPI_ACT, true, 3, 16>, p);
+    }
+  }
   if constexpr (N_TILE == 128 && EPI == EPI_ACT) {
     if (p.terms == 2) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 2>, p);
     if (p.terms == 1) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 1>, p);
@@ -1447,6 +1539,14 @@ cudaError_t conv_mma_init() {
   e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128, 1>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_ACT, true, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, true, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, true, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128, 2>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, true, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128, 1>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upconv_res_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
   if (e != cudaSuccess) return e;

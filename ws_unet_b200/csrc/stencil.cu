@@ -20,133 +20,198 @@ namespace wsu {
 namespace {
 
 // ------------------------------------------------------------------------------------------------ e11
-// One CTA = one 128-pixel row segment of one image. The 3 input rows (reflect-resolved, already scaled to [0,1]) are
-// staged in shared memory; thread (pixel lane pl = tid/8, channel group cg = tid%8) keeps its 8 x (9*cin) weights in
-// registers and walks 4 pixels. 8 threads write one pixel's 64 channels = 128 contiguous bytes per plane, a warp
-// writes 4 adjacent pixels = 512 contiguous bytes.
+// One CTA = kE11Rows rows of one 128-pixel row segment of one image. The input rows (reflect-resolved, already scaled to
+// [0,1]) are staged in shared memory; thread (pixel lane pl = tid/8, channel group cg = tid%8) keeps its 8 x 9 weights in
+// registers as fp32 pairs and walks 4 pixels per row. 8 threads write one pixel's 64 channels = one 128-byte line per plane.
+// The kernel is instruction-issue bound (ncu, round 2: 199 instructions per pixel and thread at 0.78 IPC per scheduler, 16 % of
+// the time in the staging loop's dependent global loads), so everything here is about instruction count: the output format is a
+// template parameter, row pointers are formed once per row and the four pixels use immediate offsets, the e4m3 operands come
+// from packed f32x2 arithmetic, uint8 pixels are loaded four at a time and scaled through a 256-entry table of x / 255.
 constexpr int kE11Seg = 128;   // pixels per row segment
-constexpr int kE11Rows = 8;    // rows per CTA (weights are loaded into registers once per CTA)
+constexpr int kE11Rows = 16;   // rows per CTA (weights are loaded into registers once per CTA)
+constexpr int kE11Pitch = kE11Seg + 4;
+
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
 
 // kIn: 0 = uint8 pixels (x / 255), 1 = float32 in [0,1], 2 = uint8 pixels, LSB DIFFERENCE image (x_bar - x) / 255 = +-1/255:
 // what the reference feeds the predictor for bias correction, pixel_estimator(x_bar - x) (src/ws/estimate.py:126-127)
-template <int kIn, int CIN>
-__global__ void __launch_bounds__(256) first_conv_kernel(const void* __restrict__ img, const float* __restrict__ w,
-                                                         const float* __restrict__ bias, Act out, int segs_per_row,
-                                                         int row_groups) {
-  __shared__ float rows[CIN][kE11Rows + 2][kE11Seg + 2];
+// FMT: ACT_SPLIT or ACT_F16F8 (the two formats a full-resolution map can have)
+template <int kIn, int FMT>
+__global__ void __launch_bounds__(256, 2) first_conv_kernel(const void* __restrict__ img, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, Act out, int segs_per_row,
+                                                            int row_groups) {
+  __shared__ __align__(16) float rows[kE11Rows + 2][kE11Pitch];   // column c holds pixel x0 + c - 1
+  __shared__ float lut[256];
   const int H = out.H, W = out.W;
   const int seg = blockIdx.x % segs_per_row;
   const int y0 = ((blockIdx.x / segs_per_row) % row_groups) * kE11Rows;
   const int b = blockIdx.x / (segs_per_row * row_groups);
   const int x0 = seg * kE11Seg;
-  for (int i = threadIdx.x; i < CIN * (kE11Rows + 2) * (kE11Seg + 2); i += 256) {
-    const int col = i % (kE11Seg + 2);
-    const int r = (i / (kE11Seg + 2)) % (kE11Rows + 2);
-    const int ci = i / ((kE11Rows + 2) * (kE11Seg + 2));
-    int yy = y0 + r - 1;
-    yy = min(yy, 2 * H - 2);                                // rows past a ragged last group: keep the index valid
-    yy = yy < 0 ? -yy : (yy >= H ? 2 * H - 2 - yy : yy);  // reflect (unet.py:73)
+  const int tid = threadIdx.x;
+  auto reflect_row = [&](int r) {
+    int yy = min(y0 + r - 1, 2 * H - 2);                    // rows past a ragged last group: keep the index valid
+    return yy < 0 ? -yy : (yy >= H ? 2 * H - 2 - yy : yy);  // reflect (unet.py:73)
+  };
+  auto reflect_col = [&](int col) {
     int xx = x0 + col - 1;
     xx = xx < 0 ? -xx : (xx >= W ? 2 * W - 2 - xx : xx);
-    xx = min(max(xx, 0), W - 1);                            // columns past a ragged last segment: any valid pixel
-    const size_t o = ((size_t(b) * CIN + ci) * H + yy) * W + xx;
-    float v;
-    if constexpr (kIn == 1) v = static_cast<const float*>(img)[o];
-    else if constexpr (kIn == 2) v = __fdiv_rn((static_cast<const uint8_t*>(img)[o] & 1) ? -1.f : 1.f, 255.f);   // (x ^ 1) - x
-    else v = __fdiv_rn(float(static_cast<const uint8_t*>(img)[o]), 255.f);  // x / 255. of src/unet/evaluate.py:45
-    rows[ci][r][col] = v;
+    return min(max(xx, 0), W - 1);                          // columns past a ragged last segment: any valid pixel
+  };
+  // x / 255. of src/unet/evaluate.py:45 as an IEEE division; kIn == 2: (x ^ 1) - x = +-1
+  auto scale_u8 = [&](uint32_t px) -> float {
+    if constexpr (kIn == 2) return (px & 1u) ? -lut[1] : lut[1];
+    else return lut[px];
+  };
+  if constexpr (kIn != 1) {
+    lut[tid] = __fdiv_rn(float(tid), 255.f);
+    __syncthreads();
   }
-  const int cg = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const uint8_t* im8 = static_cast<const uint8_t*>(img) + size_t(b) * H * W;
+  const float* imf = static_cast<const float*>(img) + size_t(b) * H * W;
+  const bool vec = kIn != 1 && (W % 4 == 0) && (reinterpret_cast<uintptr_t>(img) % 4 == 0);
+  if (vec) {
+    // interior columns as uchar4 groups (a group lies entirely inside or entirely outside the image because W % 4 == 0)
+    uint32_t v[3];
+    const int g = tid & 31, r0 = tid >> 5;
+    const bool in = x0 + 4 * g < W;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int r = r0 + 8 * k;
+      if (r < kE11Rows + 2 && in) v[k] = *reinterpret_cast<const uint32_t*>(im8 + size_t(reflect_row(r)) * W + x0 + 4 * g);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int r = r0 + 8 * k;
+      if (r < kE11Rows + 2) {
+        if (in) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rows[r][1 + 4 * g + j] = scale_u8((v[k] >> (8 * j)) & 0xffu);
+        } else {
+          for (int j = 0; j < 4; ++j) rows[r][1 + 4 * g + j] = scale_u8(im8[size_t(reflect_row(r)) * W + reflect_col(1 + 4 * g + j)]);
+        }
+      }
+    }
+    if (tid < 2 * (kE11Rows + 2)) {   // the two halo columns
+      const int r = tid >> 1, col = (tid & 1) ? kE11Seg + 1 : 0;
+      rows[r][col] = scale_u8(im8[size_t(reflect_row(r)) * W + reflect_col(col)]);
+    }
+  } else {
+    for (int i = tid; i < (kE11Rows + 2) * (kE11Seg + 2); i += 256) {
+      const int col = i % (kE11Seg + 2), r = i / (kE11Seg + 2);
+      const size_t o = size_t(reflect_row(r)) * W + reflect_col(col);
+      float v;
+      if constexpr (kIn == 1) v = imf[o];
+      else v = scale_u8(im8[o]);
+      rows[r][col] = v;
+    }
+  }
+  const int cg = tid & 7, pl = tid >> 3;
   // weights / accumulators as fp32 pairs: one FFMA2 advances two output channels
-  uint64_t wr[4][CIN * 9], bs[4];
+  uint64_t wr[4][9], bs[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     bs[i] = pack_f32x2(bias[cg * 8 + 2 * i], bias[cg * 8 + 2 * i + 1]);
 #pragma unroll
-    for (int t = 0; t < CIN * 9; ++t)
-      wr[i][t] = pack_f32x2(w[(cg * 8 + 2 * i) * CIN * 9 + t], w[(cg * 8 + 2 * i + 1) * CIN * 9 + t]);
+    for (int t = 0; t < 9; ++t) wr[i][t] = pack_f32x2(w[(cg * 8 + 2 * i) * 9 + t], w[(cg * 8 + 2 * i + 1) * 9 + t]);
   }
   __syncthreads();
+  // byte offset of this thread's piece inside a pixel's plane-1 row. ACT_F16F8: a pixel's plane 1 = 4 groups of [16 a2s bytes |
+  // 16 a1q bytes]; this thread owns 8 channels = bytes [8 (cg & 1), +8) of both halves of group cg / 2 (two 8-byte stores).
+  const int p1_off = FMT == ACT_F16F8 ? (cg >> 1) * 32 + (cg & 1) * 8 : cg * 16;
+  uint32_t xborder = 0;   // bit s: pixel s of this thread's row also owns reflect-halo columns
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int x = x0 + s * 32 + pl;
+    xborder |= uint32_t(x == 1 || x == W - 2) << s;
+  }
 #pragma unroll 1
-  for (int it = 0; it < kE11Rows * (kE11Seg / 32); ++it) {
-    const int ry = it / (kE11Seg / 32);
+  for (int ry = 0; ry < kE11Rows; ++ry) {
     const int y = y0 + ry;
-    const int lx = (it % (kE11Seg / 32)) * 32 + pl;
-    const int x = x0 + lx;
     if (y >= H) break;
-    if (x >= W) continue;
-    uint64_t acc[4];
+    const bool yborder = (y == 1 || y == H - 2);
+    const size_t rowpix = (size_t(b) * (H + 2) + (y + 1)) * (W + 2) + (x0 + 1 + pl);
+    __nv_bfloat16* q0 = out.base + rowpix * 64 + cg * 8;
+    uint8_t* q1 = reinterpret_cast<uint8_t*>(out.base + out.plane + rowpix * 64) + p1_off;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] = bs[i];
+    for (int s = 0; s < 4; ++s) {
+      const int lx = s * 32 + pl;
+      if (x0 + lx >= W) break;
+      uint64_t acc[4];
 #pragma unroll
-    for (int ci = 0; ci < CIN; ++ci)
+      for (int i = 0; i < 4; ++i) acc[i] = bs[i];
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const float v = rows[ci][ry + dy][lx + dx];
+          const float v = rows[ry + dy][lx + dx];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i] = fma2_bcast(v, wr[i][ci * 9 + dy * 3 + dx], acc[i]);
+          for (int i = 0; i < 4; ++i) acc[i] = fma2_bcast(v, wr[i][dy * 3 + dx], acc[i]);
         }
-    uint32_t h[4], l[4];
-    if (out.fmt == ACT_F16F8) {
-      // plane 0: 8 fp16 values; plane 1: this thread's 8 channels of the e4m3 correction operands - l[0..1] = a2s bytes,
-      // l[2..3] = a1q bytes; they land 16 bytes apart inside their 16-channel group (see the store below)
-      float v[8];
+      uint4 vh, v1;
+      uint32_t h[4], l[4];
+      if constexpr (FMT == ACT_F16F8) {
+        // plane 0: 8 fp16 values; plane 1: l[0..1] = the 8 a2s bytes e4m3((v - fp16 v) 2^14), l[2..3] = the 8 a1q bytes e4m3(8 v).
+        // (v - h) 2^14 = fma(h, -2^14, v 2^14) exactly: v - h is representable and the scale is a power of two.
+        const uint64_t kA2 = pack_f32x2(kF8ScaleA2, kF8ScaleA2), kNegA2 = pack_f32x2(-kF8ScaleA2, -kF8ScaleA2);
+        const uint64_t kA1 = pack_f32x2(kF8ScaleA1, kF8ScaleA1);
+        uint32_t a2[4], a1[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        unpack_f32x2(acc[i], v[2 * i], v[2 * i + 1]);
-        v[2 * i] = fmaxf(v[2 * i], 0.f);
-        v[2 * i + 1] = fmaxf(v[2 * i + 1], 0.f);
-        h[i] = cvt_f16x2(v[2 * i], v[2 * i + 1]);
-      }
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&h[2 * i]));
-        const float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&h[2 * i + 1]));
-        l[i] = cvt_e4m3x2((v[4 * i] - a01.x) * kF8ScaleA2, (v[4 * i + 1] - a01.y) * kF8ScaleA2) |
-               (cvt_e4m3x2((v[4 * i + 2] - a23.x) * kF8ScaleA2, (v[4 * i + 3] - a23.y) * kF8ScaleA2) << 16);
-        l[2 + i] = cvt_e4m3x2(v[4 * i] * kF8ScaleA1, v[4 * i + 1] * kF8ScaleA1) |
-                   (cvt_e4m3x2(v[4 * i + 2] * kF8ScaleA1, v[4 * i + 3] * kF8ScaleA1) << 16);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float a0, a1;
-        unpack_f32x2(acc[i], a0, a1);
-        split_pack2(fmaxf(a0, 0.f), fmaxf(a1, 0.f), h[i], l[i]);
-      }
-    }
-    const uint4 vh = make_uint4(h[0], h[1], h[2], h[3]), vl = make_uint4(l[0], l[1], l[2], l[3]);
-    // ACT_F16F8: a 16-channel group is shared by two neighbouring lanes (even cg: channels 0-7 of the group, odd cg: 8-15). They
-    // swap halves so that the even lane holds the group's 16 a2s bytes and the odd lane its 16 a1q bytes: one 16-byte store each.
-    uint4 v1 = vl;
-    if (out.fmt == ACT_F16F8) {
-      const bool odd = cg & 1;
-      const uint32_t s0 = odd ? vl.x : vl.z, s1 = odd ? vl.y : vl.w;          // odd sends its a2s, even its a1q
-      const unsigned am = __activemask();   // lanes of pixels right of a ragged row segment have left the iteration (both lanes of a pair)
-      const uint32_t r0 = __shfl_xor_sync(am, s0, 1), r1 = __shfl_xor_sync(am, s1, 1);
-      v1 = odd ? make_uint4(r0, r1, vl.z, vl.w) : make_uint4(vl.x, vl.y, r0, r1);
-    }
-    // pix: element offset of (pixel, channel 0) in a plane
-    auto store_planes = [&](size_t pix) {
-      *reinterpret_cast<uint4*>(out.base + pix + cg * 8) = vh;
-      if (out.fmt == ACT_F16F8) {
-        // plane 1 of a pixel = 4 groups of [16 a2s bytes | 16 a1q bytes]: byte offset (cg / 2) * 32 + (cg % 2) * 16 = cg * 16
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out.base + out.plane + pix) + cg * 16) = v1;
+        for (int i = 0; i < 4; ++i) {
+          float v0, v1f;
+          unpack_f32x2(acc[i], v0, v1f);
+          const uint64_t v = pack_f32x2(fmaxf(v0, 0.f), fmaxf(v1f, 0.f));
+          unpack_f32x2(v, v0, v1f);
+          h[i] = cvt_f16x2(v0, v1f);
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+          float r0, r1, s0, s1;
+          unpack_f32x2(fma2(pack_f32x2(hf.x, hf.y), kNegA2, mul2(v, kA2)), r0, r1);
+          unpack_f32x2(mul2(v, kA1), s0, s1);
+          a2[i] = cvt_e4m3x2(r0, r1);
+          a1[i] = cvt_e4m3x2(s0, s1);
+        }
+        l[0] = a2[0] | (a2[1] << 16); l[1] = a2[2] | (a2[3] << 16);
+        l[2] = a1[0] | (a1[1] << 16); l[3] = a1[2] | (a1[3] << 16);
       } else {
-        *reinterpret_cast<uint4*>(out.base + out.plane + pix + cg * 8) = vl;
-      }
-    };
-    store_planes(((size_t(b) * (H + 2) + (y + 1)) * (W + 2) + (x + 1)) * out.C);
-    if (y == 1 || x == 1 || y == H - 2 || x == W - 2) {   // reflect-halo duplicates (border pixels only)
-      int ys[3], xs[3];
-      const int ny = halo_targets(y, H, ys), nx = halo_targets(x, W, xs);
-      for (int iy = 0; iy < ny; ++iy)
-        for (int ix = 0; ix < nx; ++ix) {
-          if (iy == 0 && ix == 0) continue;
-          store_planes(((size_t(b) * (H + 2) + ys[iy]) * (W + 2) + xs[ix]) * out.C);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float a0, a1;
+          unpack_f32x2(acc[i], a0, a1);
+          split_pack2(fmaxf(a0, 0.f), fmaxf(a1, 0.f), h[i], l[i]);
         }
+      }
+      vh = make_uint4(h[0], h[1], h[2], h[3]);
+      v1 = make_uint4(l[0], l[1], l[2], l[3]);
+      // d0 / d1: this thread's plane-0 / plane-1 address for some pixel
+      auto store_planes = [&](__nv_bfloat16* d0, uint8_t* d1) {
+        *reinterpret_cast<uint4*>(d0) = vh;
+        if constexpr (FMT == ACT_F16F8) {
+          *reinterpret_cast<uint2*>(d1) = make_uint2(v1.x, v1.y);
+          *reinterpret_cast<uint2*>(d1 + 16) = make_uint2(v1.z, v1.w);
+        } else {
+          *reinterpret_cast<uint4*>(d1) = v1;
+        }
+      };
+      store_planes(q0 + s * 32 * 64, q1 + s * 32 * 128);
+      if (yborder || ((xborder >> s) & 1)) {   // reflect-halo duplicates (border pixels only)
+        const int x = x0 + lx;
+        int ys[3], xs[3];
+        const int ny = halo_targets(y, H, ys), nx = halo_targets(x, W, xs);
+        for (int iy = 0; iy < ny; ++iy)
+          for (int ix = 0; ix < nx; ++ix) {
+            if (iy == 0 && ix == 0) continue;
+            const size_t pix = ((size_t(b) * (H + 2) + ys[iy]) * (W + 2) + xs[ix]) * 64;
+            store_planes(out.base + pix + cg * 8, reinterpret_cast<uint8_t*>(out.base + out.plane + pix) + p1_off);
+          }
+      }
     }
   }
 }
@@ -1074,15 +1139,20 @@ cudaError_t launch_first_conv(const void* img, int img_kind, int cin, const floa
                               cudaStream_t stream) {
   const bool img_is_float = img_kind == 1;
   if (cin == 1) {
+    if (out.C != 64 || out.fmt == ACT_F16) return cudaErrorInvalidValue;   // e11 is a 64-channel full-resolution map
     const int segs = (out.W + kE11Seg - 1) / kE11Seg;
     const int groups = (out.H + kE11Rows - 1) / kE11Rows;
     const int grid = out.B * groups * segs;
-    if (img_kind == 1)
-      first_conv_kernel<1, 1><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);
-    else if (img_kind == 2)
-      first_conv_kernel<2, 1><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);
-    else
-      first_conv_kernel<0, 1><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);
+    const bool f8 = out.fmt == ACT_F16F8;
+#define WSU_E11(KIN)                                                                                         \
+  do {                                                                                                       \
+    if (f8) first_conv_kernel<KIN, ACT_F16F8><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);   \
+    else first_conv_kernel<KIN, ACT_SPLIT><<<grid, 256, 0, stream>>>(img, w, bias, out, segs, groups);      \
+  } while (0)
+    if (img_kind == 1) WSU_E11(1);
+    else if (img_kind == 2) WSU_E11(2);
+    else WSU_E11(0);
+#undef WSU_E11
     return cudaGetLastError();
   }
   if (img_kind == 2) return cudaErrorInvalidValue;   // the LSB-difference input exists for single-channel images only

@@ -66,7 +66,8 @@ int wsu_commit_weights(wsu_handle h);
  *                       set_precision / calibrate_precision; wsu_get_info "precision" reports what is active);
  *          "upconv_resident" (default 1: transposed convs keep their weights in shared memory; 0: per-phase kernel);
  *          "halo" (default 1: 3x3 layers load one haloed box per channel block; 0: per-tap reload kernel);
- *          "tma_store" (default 0; 1: interior boxes of the 3x3 layers leave through TMA tensor stores - measured neutral);
+ *          "tma_store" (default 1: interior boxes of the 3x3 layers leave through TMA tensor stores, bit-identical, 1-3 % of the chain);
+ *          "w_resident" (default 1: under precision 3 the layers with one input channel block keep all nine taps' weights in shared memory);
  *          "alias_buffers" (default 1: feature maps with disjoint lifetimes share arena bytes; 0 for layer inspection);
  *          "profile" (1: record CUDA events around every layer launch of the last micro-batch) */
 int wsu_set_option(wsu_handle h, const char* key, int64_t value);

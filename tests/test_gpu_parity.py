@@ -361,6 +361,7 @@ def test_kernel_variants_agree(cuda_dev):
         lib.wsu_set_option(h, b'fuse_e11', 0)
         assert torch.equal(y_fused, m(inp))
     # interior boxes written by TMA tensor stores out of the staging buffer instead of per-lane stores: same bits
+    lib.wsu_set_option(h, b'tma_store', 0)
     y_plain = m(xd)
     lib.wsu_set_option(h, b'tma_store', 1)
     assert torch.equal(m(xd), y_plain)
@@ -368,6 +369,7 @@ def test_kernel_variants_agree(cuda_dev):
     y_tma = m(big)
     lib.wsu_set_option(h, b'tma_store', 0)
     assert torch.equal(m(big), y_tma)
+    lib.wsu_set_option(h, b'tma_store', 1)
     with pytest.raises(ValueError):
         _native.check(lib.wsu_set_option(h, b'no_such_option', 1))
 

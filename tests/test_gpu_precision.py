@@ -106,6 +106,28 @@ def test_reduced_plan_ws_properties(cuda_dev, mode):
     assert torch.equal(W.ws_estimate(d, m, weighted=1, clip=False), b3)
 
 
+def test_resident_weights_and_tma_stores_change_no_bit(cuda_dev):
+    """Under 'fp16x1_f8' e12 / d42 keep their weights in shared memory (option w_resident) and interior boxes leave through
+    TMA stores (option tma_store): both are data-movement choices, every output bit must stay, ragged sizes included."""
+    import ws_unet_b200 as W
+    from ws_unet_b200 import _native
+    lib = _native.load()
+    torch.manual_seed(7)
+    m = W.get_model('unet_2', 1).to(cuda_dev).set_precision('fp16x1_f8')
+    h = m.native_handle(cuda_dev)
+    for shape in ((3, 1, 64, 96), (2, 1, 136, 72)):
+        img = torch.randint(0, 256, shape, dtype=torch.uint8, device=cuda_dev)
+        outs = {}
+        for res in (0, 1):
+            for tma in (0, 1):
+                _native.check(lib.wsu_set_option(h, b'w_resident', res))
+                _native.check(lib.wsu_set_option(h, b'tma_store', tma))
+                outs[(res, tma)] = (m(img), W.ws_estimate(img, m, weighted=1, clip=False, correct_bias=True))
+        ref = outs[(0, 0)]
+        for k, v in outs.items():
+            assert torch.equal(v[0], ref[0]) and torch.equal(v[1], ref[1]), k
+
+
 def test_calibration_accepts_and_rejects(cuda_dev, capsys):
     """calibrate_precision keeps a reduced plan only when its predictions stay within the budget of the three-term plan.
     Random-init weights (the benchmark's model) route almost nothing through the deep path -> the one-term plan passes; a

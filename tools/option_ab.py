@@ -1,4 +1,4 @@
-"""A/B of one wsu_set_option key on the per-layer times of the fp16x1 plan (CUDA events, min of reps).
+"""A/B of one wsu_set_option key on the per-layer times (CUDA events, median of 2*reps passes, variants interleaved).
 Usage (on a B200): python tools/option_ab.py <key> <value_a> <value_b> [images=32] [reps=3] [precision=fp16x1]"""
 import ctypes
 import sys
@@ -20,23 +20,24 @@ imgs = torch.randint(0, 256, (n, 1, 512, 512), dtype=torch.uint8, device=dev)
 lib = _native.load()
 model.set_micro_batch(n, dev)
 h = model.native_handle(dev)
-res, outs = {}, {}
-for v in (va, vb, va, vb):
+res, outs = {va: [], vb: []}, {}
+for v in (va, vb):
     _native.check(lib.wsu_set_option(h, key.encode(), v))
     outs[v] = W.ws_estimate(imgs[:4], model, weighted=0, clip=False)
-    lib.wsu_set_option(h, b'profile', 1)
-    acc = res.get(v)
-    for _ in range(reps):
+    W.ws_estimate(imgs, model, weighted=0, clip=True, crop=1)          # warm-up of this variant's kernels
+lib.wsu_set_option(h, b'profile', 1)
+for rep in range(2 * reps):                 # A B B A A B B A ...: clock drift inside the process hits both variants alike
+    for v in ((va, vb) if rep % 2 == 0 else (vb, va)):
+        _native.check(lib.wsu_set_option(h, key.encode(), v))
         W.ws_estimate(imgs, model, weighted=0, clip=True, crop=1)
         torch.cuda.synchronize()
         buf = (ctypes.c_float * 64)()
         k = lib.wsu_profile_read(h, buf, 64)
-        cur = [buf[i] for i in range(k)]
-        acc = cur if acc is None else [min(a, c) for a, c in zip(acc, cur)]
-    res[v] = acc
-    names = [lib.wsu_profile_name(h, i).decode() for i in range(len(acc))]
-    lib.wsu_set_option(h, b'profile', 0)
-print(f'{key}: {va} vs {vb}; {n} images, {mode}; results equal: {torch.equal(outs[va], outs[vb])}')
+        res[v].append([buf[i] for i in range(k)])
+names = [lib.wsu_profile_name(h, i).decode() for i in range(len(res[va][0]))]
+lib.wsu_set_option(h, b'profile', 0)
+med = {v: [sorted(r[i] for r in res[v])[len(res[v]) // 2] for i in range(len(names))] for v in (va, vb)}
+print(f'{key}: {va} vs {vb}; {n} images, {mode}, median of {2 * reps} interleaved passes; results equal: {torch.equal(outs[va], outs[vb])}')
 for i, nm in enumerate(names):
-    print(f'{nm:9s} {res[va][i]:8.3f} {res[vb][i]:8.3f}  {100 * (res[vb][i] / res[va][i] - 1):+6.1f} %')
-print(f'total     {sum(res[va]):8.3f} {sum(res[vb]):8.3f}  {100 * (sum(res[vb]) / sum(res[va]) - 1):+6.1f} %')
+    print(f'{nm:9s} {med[va][i]:8.3f} {med[vb][i]:8.3f}  {100 * (med[vb][i] / med[va][i] - 1):+6.1f} %')
+print(f'total     {sum(med[va]):8.3f} {sum(med[vb]):8.3f}  {100 * (sum(med[vb]) / sum(med[va]) - 1):+6.1f} %')

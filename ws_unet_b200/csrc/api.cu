@@ -239,11 +239,13 @@ struct wsu_context {
   // fp16 (hi, lo) / fp16 hi-only weights = 2 / 1 MMAs per MAC and half the activation bytes; the full-resolution layers
   // (e12, d41, d42), whose rounding reaches the output directly, stay three-term. Whether a plan keeps a given model inside
   // the 1e-3 px bar depends on its weights: UNet.calibrate_precision() measures it against plan 0 and picks.
-  int epi_warps = 8;          // option "epi_warps" (8 | 16): epilogue warps per CTA of the CTA-pair 3x3 kernel (activation epilogue)
-  int tma_store = 0;          // option "tma_store": interior boxes of the 3x3 halo kernels are written by TMA tensor stores out of
+  int w_resident = 1;         // option "w_resident": e12 / d42 under the fp16 + fp8 plan keep their 72 KB of weights in shared memory
+  int tma_store = 1;          // option "tma_store": interior boxes of the 3x3 halo kernels are written by TMA tensor stores out of
                               // the staging buffer (one cp.async.bulk.tensor per 32 x 32 chunk and plane instead of 4 LDS + 4 STG per
-                              // lane). Bit-identical, measured neutral (e12 -0.7 %, d41 -1.8 %, e21 / e22 +3-4 %, total +0.4 %): the
-                              // store path costs its bytes, not its instructions. Off by default, kept for A/B runs.
+                              // lane). Bit-identical. Measured with the variants interleaved pass by pass: -1.3 % of the chain under
+                              // the three-term plan, -3.1 % under fp16x1, -1.8 % under fp16x1_f8 (e12 -5..7 %, e21 -10 %); the
+                              // first A/B of this option ran the variants one after the other and read as neutral because the
+                              // clocks sag during a process.
   bool alias_buffers = true;  // option "alias_buffers": feature maps with disjoint lifetimes share arena bytes
   // 3: plan 2, and the full-resolution 3x3 layers (e12, d41's skip half, d42) read ACT_F16F8 maps: one fp16 MMA for the main
   // product and ONE e4m3 MMA for both correction terms (two MMA times instead of three at ~15 significant bits - this part
@@ -595,7 +597,7 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
     p.a_collector = h->a_collector;
     p.dbg = h->dbg;
     p.tma_store = (h->tma_store && halo && epi == EPI_ACT && !p.upsample) ? 1 : 0;
-    p.epi_warps = h->epi_warps;
+    p.w_resident = h->w_resident;
     if (nimg != pl.mb) {
       p.B = nimg;
       p.total_tiles = nimg * p.tiles_y * p.tiles_x * p.n_tiles * p.npos;
@@ -812,9 +814,8 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
     }
     return WSU_OK;
   }
-  if (!std::strcmp(key, "epi_warps")) {
-    if (value != 8 && value != 16) return fail(WSU_ERR_INVALID, "epi_warps must be 8 or 16");
-    h->epi_warps = int(value);
+  if (!std::strcmp(key, "w_resident")) {
+    h->w_resident = value != 0;
     return WSU_OK;
   }
   if (!std::strcmp(key, "tma_store")) {

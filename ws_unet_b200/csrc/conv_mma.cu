@@ -221,58 +221,6 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
   }
 }
 
-// The same store with HALF the staging bytes (1 KB per warp): the chunk leaves in two 16-channel halves of 32-byte rows; two
-// consecutive lanes write one pixel's 32 bytes = one full sector, a store instruction covers 16 pixels. Used by the kernels
-// with sixteen epilogue warps, whose staging area would not fit next to the operand rings otherwise.
-constexpr int kNarrowPerWarp = 32 * 32;
-__device__ __forceinline__ void store_chunk_narrow(const Act& o, uint8_t* scratch, int lane, int row0, int c0,
-                                                   const uint32_t (&h)[16], const uint32_t (&l)[16], const BoxGeo& g) {
-  const int planes = o.fmt == ACT_F16 ? 1 : 2;
-  const int piece = lane & 1;
-  // both pixels this lane re-reads: q = (lane >> 1) + 16 i
-  size_t off[2];
-  bool ok[2], edge = false;
-  int oy[2], ox[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    ok[i] = g.pixel(row0 + (lane >> 1) + 16 * i, oy[i], ox[i]);
-    off[i] = ((size_t(g.b) * (o.H + 2) + (oy[i] + 1)) * (o.W + 2) + (ox[i] + 1)) * o.C;
-    edge |= ok[i] && (oy[i] == 1 || ox[i] == 1 || oy[i] == o.H - 2 || ox[i] == o.W - 2);
-  }
-  const bool border = __any_sync(0xffffffffu, edge);
-#pragma unroll
-  for (int plane = 0; plane < 2; ++plane) {
-    if (plane >= planes) break;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      __syncwarp();
-      uint4* mine = reinterpret_cast<uint4*>(scratch + lane * 32);
-      const int wsw = (lane >> 2) & 1;
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int w0 = 8 * half + 4 * q;
-        mine[q ^ wsw] = plane ? make_uint4(l[w0], l[w0 + 1], l[w0 + 2], l[w0 + 3]) : make_uint4(h[w0], h[w0 + 1], h[w0 + 2], h[w0 + 3]);
-      }
-      __syncwarp();
-      __nv_bfloat16* base = o.base + (plane ? o.plane : 0) + c0 + half * 16 + piece * 8;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int q = (lane >> 1) + 16 * i;
-        const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * 32 + ((piece ^ ((q >> 2) & 1)) << 4));
-        if (!border) {
-          if (ok[i]) *reinterpret_cast<uint4*>(base + off[i]) = v;
-        } else if (ok[i]) {
-          int ys[3], xs[3];
-          const int ny = halo_targets(oy[i], o.H, ys), nx = halo_targets(ox[i], o.W, xs);
-          for (int iy = 0; iy < ny; ++iy)
-            for (int ix = 0; ix < nx; ++ix)
-              *reinterpret_cast<uint4*>(base + ((size_t(g.b) * (o.H + 2) + ys[iy]) * (o.W + 2) + xs[ix]) * o.C) = v;
-        }
-      }
-    }
-  }
-}
-
 // STACKED (Cout = 64 layers of the halo kernel): the accumulator is 128 columns wide, columns [0,64) hold
 // (Ahi + Alo) * Whi and columns [64,128) hold Ahi * Wlo of the same 64 output channels; they are summed here.
 // Under the fp16 + fp8 scheme the second half holds the correction sum scaled by a power of two (corr_scale undoes it).
@@ -293,19 +241,15 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&f)[32], float
   }
 }
 
-// [cc0, cc1): the 32-channel chunks of the box this warp finishes (all of them with eight epilogue warps; NARROW = the
-// sixteen-warp kernels, where two warps share a box quarter and stage through 1 KB each)
-template <int N_TILE, int EPI, bool STACKED = false, bool NARROW = false>
+template <int N_TILE, int EPI, bool STACKED = false>
 __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* sBias, uint32_t tbase, int b, int y, int x,
                                        bool valid, int nt, int pos, int tx, int ty, int pool_xor, WsAcc& acc,
-                                       const BoxGeo& geo, uint8_t* scratch, int lane, int row0, int cc0 = 0,
-                                       int cc1 = N_TILE / 32) {
+                                       const BoxGeo& geo, uint8_t* scratch, int lane, int row0) {
   if (p.dbg & 4) return;   // WSU_DBG=4: no epilogue work at all (timing experiment: what the MMA pipeline alone takes)
   if constexpr (EPI == EPI_ACT) {
-    StoreMap smap;
-    if constexpr (!NARROW) smap = make_store_map(p.out, geo, lane, row0);
+    const StoreMap smap = make_store_map(p.out, geo, lane, row0);
 #pragma unroll 1
-    for (int cc = cc0; cc < cc1; ++cc) {
+    for (int cc = 0; cc < N_TILE / 32; ++cc) {
       const int n0 = nt * N_TILE + cc * 32;
       float f[32];
       load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f, (p.dbg & 8) ? 0.f : p.corr_scale);   // WSU_DBG=8: correction MMA off (diagnostic)
@@ -328,10 +272,7 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
 #pragma unroll
         for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
       }
-      if (!(p.dbg & 2)) {
-        if constexpr (NARROW) store_chunk_narrow(p.out, scratch, lane, row0, n0, h, l, geo);
-        else store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap, p.tma_store ? &p.tmapOut : nullptr, p.dbg);
-      }
+      if (!(p.dbg & 2)) store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap, p.tma_store ? &p.tmapOut : nullptr, p.dbg);
       if (p.do_pool && !(p.dbg & 1)) {
         // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16). Each exchange moves
         // only the half the partner will keep, so the four lanes of a quad end up with 8 channels each of the pooled
@@ -989,18 +930,22 @@ cudaError_t launch_halo_t(const ConvParams& p, int num_sms, cudaStream_t stream)
 // TERMS = MMAs per algorithmic MAC. 3: split-bf16 activations (hi, lo planes) x split-bf16 weights, hi*hi + hi*lo + lo*hi.
 // 2 / 1: the input map is ONE fp16 plane (ACT_F16) against fp16 (hi, lo) / fp16 hi-only weights - the layers the precision
 // plan (api.cu, option "precision") runs below three terms. Half-size boxes: the ring holds six of them.
-template <int N_TILE, int TERMS = 3>
+// RES: the layer's whole weight set stays in shared memory (fp16 + fp8 layers with ONE input channel block, e12 / d42:
+// 9 taps x (4 KB fp16 + 4 KB e4m3) per CTA = 72 KB, about what the ring took). These layers stream 46 KB of boxes and 36 KB
+// of weights per box from L2 (8.2 TB/s for the loads alone, WSU_DBG timings) and everything crosses the SM's shared-memory
+// data path, which bounds them: keeping the weights removes 44 % of the L2 -> SM bytes and 7 % of the shared-memory traffic.
+template <int N_TILE, int TERMS = 3, bool RES = false>
 struct H2Cfg {
   static constexpr bool STACKED = (N_TILE == 64);
   static constexpr int M_SUB = 2;                 // box slots per item (x 2 CTAs = 4 boxes share one weight pass)
   static constexpr int ACC_W = 128;
   static constexpr int A_BYTES = TERMS == 3 ? kHaloABytes : kHaloABytes / 2;
   static constexpr int SA = TERMS == 3 ? 3 : (TERMS == 2 ? 4 : 6);   // fp16 boxes are 22.5 KB: an even count keeps the weight ring 1024-byte aligned
-  static constexpr int W_SLOT = TERMS == 1 ? 8192 : 16384;   // [X tile 8 KB][Y tile 4 KB (stacked) | Z tile 8 KB]
+  static constexpr int W_SLOT = (TERMS == 1 || RES) ? 8192 : 16384;   // [X tile 8 KB][Y tile 4 KB (stacked) | Z tile 8 KB]; RES: [fp16 4 KB][e4m3 4 KB]
   static constexpr int W_BYTES = STACKED ? 12288 : (TERMS == 1 ? 8192 : 16384);
   // a tap's weights are consumed in 2 x 4 MMAs: ~1500 / 1000 / 540 cycles with 3 / 2 / 1 terms, against an L2 -> shared
   // latency of ~2500 cycles per bulk copy: the ring has to be deeper the fewer terms a tap takes
-  static constexpr int SW = TERMS == 3 ? 4 : (TERMS == 2 ? 6 : 8);
+  static constexpr int SW = RES ? 9 : (TERMS == 3 ? 4 : (TERMS == 2 ? 6 : 8));
   static_assert((SA * A_BYTES) % 1024 == 0, "pre-swizzled weight tiles need a 1024-byte aligned ring");
   static constexpr int BIAS_BYTES = (N_TILE == 64) ? 256 : 4096;
   static constexpr int SMEM = SA * A_BYTES + SW * W_SLOT + kScratchBytes + 1024 + BIAS_BYTES + 512 /*barriers*/;
@@ -1016,18 +961,15 @@ __device__ __forceinline__ int block_mode(const ConvParams& p, int c) {
   return p.f8_blocks ? MODE_F8 : MODE_SPLIT3;
 }
 
-// EW = epilogue warps per CTA. 8: warp group g finishes box g of the item, every 32-channel chunk. 16: four groups, group g
-// finishes half the chunks of box g & 1 - under the reduced plans an item's MMAs take a third to a half of the three-term time
-// and the epilogue (TMEM read, bias, ReLU, format conversion, staging, stores, pooling) had become the longer leg of the
-// pipeline (WSU_DBG=4 timings: e12 1.32 ms with, 0.92 ms without epilogue work).
-template <int N_TILE, int EPI, bool COLL = true, int TERMS = 3, int EW = 8>
-__global__ void __launch_bounds__((3 + EW) * 32, 1) conv_halo2_kernel(const __grid_constant__ ConvParams p) {
+// Tried and dropped (profiles/r02_ab_epilogue_warps_tma_store.log): sixteen epilogue warps per CTA (two per box quarter, half
+// the chunks each, 1 KB of staging per warp) - bit-identical and 13 % slower over the chain: these kernels are bound by the
+// shared-memory data path, which more warps do not widen, and 608 threads leave 96 registers per thread (spills).
+template <int N_TILE, int EPI, bool COLL = true, int TERMS = 3, bool RES = false>
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __grid_constant__ ConvParams p) {
   static_assert(TERMS == 3 || N_TILE == 128, "the one- and two-term variants exist for the Cout >= 128 layers only");
-  static_assert(EW == 8 || (EW == 16 && EPI == EPI_ACT), "sixteen epilogue warps: activation epilogue only");
-  using C = H2Cfg<N_TILE, TERMS>;
+  static_assert(!RES || (N_TILE == 64 && TERMS == 3), "resident weights: fp16 + fp8 layers with one channel block");
+  using C = H2Cfg<N_TILE, TERMS, RES>;
   constexpr int M_SUB = C::M_SUB;
-  constexpr int kThreadsK = (3 + EW) * 32;
-  constexpr int kWeightWarp = 2 + EW;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1062,11 +1004,11 @@ __global__ void __launch_bounds__((3 + EW) * 32, 1) conv_halo2_kernel(const __gr
     // the weight relay it had made every layer with fewer than three MMAs per MAC wait on the relay, not on the tensor pipe.)
     for (int i = 0; i < C::SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < C::SW; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * EW); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 16); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
-  for (int i = threadIdx.x; i < p.cout && i < C::BIAS_BYTES / 4; i += kThreadsK) sBias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.cout && i < C::BIAS_BYTES / 4; i += kHaloThreads) sBias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / peer-credited TMA
@@ -1104,12 +1046,25 @@ __global__ void __launch_bounds__((3 + EW) * 32, 1) conv_halo2_kernel(const __gr
         }
       }
     }
-  } else if (warp == kWeightWarp) {
+  } else if (warp == 10) {
     // ===================================================== weight half-tiles of this CTA
     if (elect_one()) {
       int ws = 0;
       uint32_t wph = 0;
       const int chunks = p.cblocks * 9;
+      if constexpr (RES) {
+        // all nine taps once: this CTA's 32 rows of the fp16 tile and of the e4m3 tile of every tap (n_tiles == 1, cblocks == 1)
+        if (pair < items) {
+          for (int q = 0; q < 9; ++q) {
+            uint8_t* dst = sW + q * C::W_SLOT;
+            const uint32_t full_leader = mapa_u32(smem_u32(&w_full[q]), 0);
+            const int row0 = q * 2 * N_TILE;
+            if (leader) mbar_arrive_expect_tx(&w_full[q], 2 * 8192);
+            tma_load_2d_2sm(dst, &p.tmapW32, full_leader, 0, row0 + int(rank) * 32);
+            tma_load_2d_2sm(dst + 4096, &p.tmapW32, full_leader, 0, row0 + 64 + int(rank) * 32);
+          }
+        }
+      } else
       for (int item = pair; item < items; item += npairs) {
         const int nt = item % p.n_tiles;
         for (int q = 0; q < chunks; ++q) {
@@ -1178,12 +1133,15 @@ __global__ void __launch_bounds__((3 + EW) * 32, 1) conv_halo2_kernel(const __gr
 #pragma unroll
                     for (int tt = 0; tt < GT; ++tt) {
                       const int tap = GT * g + tt;
-                      if (j == 0) {
+                      if constexpr (RES) {
+                        wslot[tt] = tap;
+                        if (j == 0 && item == pair) mbar_wait(&w_full[tap], 0);   // the tap's weights have landed (first item only)
+                      } else if (j == 0) {
                         wslot[tt] = ws;
                         mbar_wait(&w_full[ws], wph);
                         if (++ws == C::SW) { ws = 0; wph ^= 1; }
                       }
-                      const uint32_t w_x = smem_u32(sW + wslot[tt] * C::W_SLOT), w_y = w_x + 8192;
+                      const uint32_t w_x = smem_u32(sW + wslot[tt] * C::W_SLOT), w_y = w_x + (RES ? 4096 : 8192);
                       const uint32_t tap_off = uint32_t((tap / 3) * (kHaloTW + 2) + (tap % 3)) * 128;
                       if (tap == 0) {
                         mbar_wait(&a_full[as], aph);
@@ -1228,14 +1186,18 @@ __global__ void __launch_bounds__((3 + EW) * 32, 1) conv_halo2_kernel(const __gr
                           }
                         }
                       }
-                      if (j == nslot - 1) umma_commit_2sm(&w_empty[wslot[tt]], 3);
+                      if constexpr (!RES) {
+                        if (j == nslot - 1) umma_commit_2sm(&w_empty[wslot[tt]], 3);
+                      }
                       if (tap == 8) umma_commit_2sm(&a_empty[a_slot[j]], 3);
                     }
                   }
                 }
               }
             };
-            if constexpr (C::STACKED) {
+            if constexpr (RES) {
+              issue_block(std::integral_constant<int, MODE_F8>{});
+            } else if constexpr (C::STACKED) {
               const int mode = block_mode(p, c);
               if (mode == MODE_F8) issue_block(std::integral_constant<int, MODE_F8>{});
               else if (mode == MODE_F16_1) issue_block(std::integral_constant<int, MODE_F16_1>{});
@@ -1253,9 +1215,7 @@ __global__ void __launch_bounds__((3 + EW) * 32, 1) conv_halo2_kernel(const __gr
   } else {
     // ===================================================== epilogue warps (each CTA finishes its own boxes)
     const int quad = warp & 3;
-    const int grp = ((warp - 2) >> 2) & 1;          // box slot of the item
-    const int part = (warp - 2) >> 3;               // EW == 16: which half of the box's chunks
-    constexpr int NCH = N_TILE / 32, CPP = NCH / (EW / 8);
+    const int grp = (warp - 2) >> 2;
     const int row = quad * 32 + lane;
     const int ty = row / kHaloTW, tx = row % kHaloTW;
     int acs = 0;
@@ -1276,9 +1236,8 @@ __global__ void __launch_bounds__((3 + EW) * 32, 1) conv_halo2_kernel(const __gr
           const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acs * kAccCols + j * C::ACC_W);
           WsAcc acc;
           const BoxGeo geo{bc.b, bc.y0, bc.x0, 3, p.H, p.W, 0, 0};
-          epilogue_box<N_TILE, EPI, C::STACKED, EW == 16>(p, sBias, tbase, bc.b, y, x, valid, nt, 0, tx, ty, kHaloTW, acc, geo,
-                                                          sScratch + (warp - 2) * (EW == 16 ? kNarrowPerWarp : kScratchPerWarp),
-                                                          lane, quad * 32, part * CPP, (part + 1) * CPP);
+          epilogue_box<N_TILE, EPI, C::STACKED>(p, sBias, tbase, bc.b, y, x, valid, nt, 0, tx, ty, kHaloTW, acc, geo,
+                                                sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32);
           if constexpr (EPI == EPI_HEAD) {
             if (p.partials) {
               const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1), wb = warp_sum(acc.wb);
@@ -1313,10 +1272,10 @@ template <int N_TILE, int EPI>
 cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   int pairs = num_sms / 2;
   if (pairs > p.total_items) pairs = p.total_items;
-  const bool wide = EPI == EPI_ACT && p.epi_warps == 16 && (N_TILE == 64 || p.a_collector);
+  const bool res = N_TILE == 64 && p.w_resident && p.f8_blocks && p.cblocks == 1 && !p.src0_f16 && p.n_tiles == 1;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(wide ? 19 * 32 : kHaloThreads);
+  cfg.blockDim = dim3(kHaloThreads);
   cfg.dynamicSmemBytes = (N_TILE == 128 && p.terms == 2) ? H2Cfg<128, 2>::SMEM : (N_TILE == 128 && p.terms == 1) ? H2Cfg<128, 1>::SMEM : H2Cfg<N_TILE>::SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -1326,14 +1285,11 @@ cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if constexpr (EPI == EPI_ACT) {
-    if (wide) {
-      if constexpr (N_TILE == 128) {
-        if (p.terms == 2) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 2, 16>, p);
-        if (p.terms == 1) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 1, 16>, p);
-      }
+  if constexpr (N_TILE == 64) {
+    if (res) {
       if (p.terms != 3) return cudaErrorInvalidValue;
-      return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<N_TILE, EPI_ACT, true, 3, 16>, p);
+      cfg.dynamicSmemBytes = H2Cfg<64, 3, true>::SMEM;
+      return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<64, EPI, true, 3, true>, p);
     }
   }
   if constexpr (N_TILE == 128 && EPI == EPI_ACT) {
@@ -1540,13 +1496,10 @@ cudaError_t conv_mma_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_ACT, true, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
+  static_assert(H2Cfg<64, 3, true>::SMEM <= 232448, "resident-weight variant exceeds the shared memory of an SM");
+  e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_ACT, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64, 3, true>::SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, true, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128>::SMEM);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, true, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128, 2>::SMEM);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, true, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128, 1>::SMEM);
+  e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_HEAD, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64, 3, true>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upconv_res_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
   if (e != cudaSuccess) return e;

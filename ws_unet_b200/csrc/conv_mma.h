@@ -19,7 +19,7 @@ struct alignas(64) ConvParams {
   CUtensorMap tmapW32; // same, box = 32 rows (stacked Cout = 64 pair kernel: half of the 64-row Whi tile)
   CUtensorMap tmapOut; // destination map, box (32 ch, 8 px, 4 rows, 1 img, 1 plane), SWIZZLE_64B: TMA stores of the halo kernels
   int tma_store;       // 1: interior boxes leave through tmapOut
-  int epi_warps;       // CTA-pair 3x3 kernel, activation epilogue: 8 or 16 epilogue warps per CTA
+  int w_resident;      // fp16 + fp8 layers with one input channel block keep all nine taps' weights in shared memory
   const uint8_t* wpack;  // packed + pre-swizzled split-bf16 weights, see pack_conv_weights()
   const float* bias;     // [Cout]
   int cblocks0;          // 64-channel blocks taken from source 0

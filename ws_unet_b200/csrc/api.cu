@@ -814,6 +814,10 @@ int wsu_set_option(wsu_handle h, const char* key, int64_t value) {
     }
     return WSU_OK;
   }
+  if (!std::strcmp(key, "dbg")) {   // the WSU_DBG switches as an option, for interleaved A/B timing (tools/option_ab.py)
+    h->dbg = int(value);
+    return WSU_OK;
+  }
   if (!std::strcmp(key, "w_resident")) {
     h->w_resident = value != 0;
     return WSU_OK;

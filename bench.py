@@ -438,6 +438,31 @@ def run_ours(args):
         parity = {'max_abs_beta': d_beta, 'max_abs_px': d_px, 'max_abs_l1': d_l1, 'images': len(ref_vals), 'against': ref.kind,
                   'ok': bool(d_beta < BETA_TOL and d_px < PX_TOL), 'tolerance': {'beta': BETA_TOL, 'px': PX_TOL}}
 
+    # ---- the same step under the other precision plans (N = 1 only, after everything that is reported above): what the
+    # headline would be with the round-1 arithmetic (three MMAs per MAC everywhere) and with the intermediate plan
+    plans = None
+    if world == 1 and S == 512 and not args.images and args.precision == 'auto':
+        plans = {}
+        chosen = model.active_precision(dev)
+        for mode in ('bf16x3', 'fp16x1', 'fp16x1_f8'):
+            if mode == chosen:
+                plans[mode] = {'images_per_s': value, 'note': 'the timed region above'}
+                continue
+            model.set_precision(mode)
+            if model.active_precision(dev) != mode:
+                continue
+            for _ in range(2):
+                W.ws_estimate(imgs, model, weighted=0, clip=True, crop=1)
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(3):
+                W.ws_estimate(imgs, model, weighted=0, clip=True, crop=1)
+            p1.record()
+            torch.cuda.synchronize()
+            plans[mode] = {'images_per_s': per_gpu * 3 / (p0.elapsed_time(p1) / 1e3), 'note': '3 steps after the timed region (secondary)'}
+        model.set_precision(chosen)
+
     ncu = ncu_summary()
     line = {
         'metric': METRIC if S == 512 else f'UNet-WS {S}x{S} images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -457,6 +482,7 @@ def run_ours(args):
         'gather_check': gather_check,
         'parity': parity,
         'precision': precision['report'],
+        'precision_plans': plans,
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
                      'frac': achieved / pk['tf_sustained'],
                      'frac_step': step_tflops / pk['tf_sustained'],

@@ -144,7 +144,10 @@ int make_w_tmap(CUtensorMap* m, const void* wpack, size_t bytes, int box_rows) {
 
 // 5-D map for TMA STORES of a 32-pixel x 32-channel chunk: dims as make_act_tmap, box (32 ch, 8 px, 4 rows, 1, 1); the
 // 64-byte inner rows are XOR-swizzled (SWIZZLE_64B) exactly like the epilogue's staging buffer.
-int make_out_tmap(CUtensorMap* m, const Act& a) {
+// up = true: the map of ONE output phase of a 2x up-convolution - a warp's chunk is 2 input rows x 16 input pixels, whose
+// outputs of phase (dy, dx) sit at every second pixel of every second row: box (32 ch, 16 px, 2 rows) traversed with element
+// strides (1, 2, 2); the start coordinate carries the phase.
+int make_out_tmap(CUtensorMap* m, const Act& a, bool up = false) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return fail(WSU_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t Wp = a.W + 2, Hp = a.H + 2;
@@ -153,6 +156,10 @@ int make_out_tmap(CUtensorMap* m, const Act& a) {
   cuuint64_t strides[4] = {cuuint64_t(a.C) * 2, Wp * a.C * 2, Hp * Wp * a.C * 2, cuuint64_t(a.plane) * 2};
   cuuint32_t box[5] = {32, 8, 4, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (up) {   // boxDim counts traversed positions: ceil(32 / 2) = 16 pixels, ceil(4 / 2) = 2 rows
+    box[1] = 32; box[2] = 4;
+    estr[1] = 2; estr[2] = 2;
+  }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, a.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(WSU_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed with code " + std::to_string(int(r)));
@@ -168,6 +175,7 @@ struct HostTensor {
 struct LayerW {  // device-side packed weights of one tensor-core layer
   uint8_t* wpack = nullptr;
   float* bias = nullptr;
+  std::vector<float> bias_host;   // the uploaded bias (all zero when it was folded into the consuming layer)
   int cin = 0, cout = 0, n_tile = 0, ntaps = 0, npos = 0;
   int terms = 3;            // MMAs per MAC: 3 = split-bf16 weights against split-bf16 inputs; 2 / 1 = fp16 (hi, lo) / hi weights
                             // against ONE fp16 input plane (precision plan, see wsu_context::precision)
@@ -424,6 +432,8 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
     u.tiles_y = (u.H + 7) / 8;
     u.total_boxes = u.B * u.tiles_x * u.tiles_y;
     u.out = *out;
+    if ((rc = make_out_tmap(&u.tmapOut, *out, true))) return rc;
+    u.zero_bias = std::all_of(lw.bias_host.begin(), lw.bias_host.end(), [](float v) { return v == 0.f; }) ? 1 : 0;
     ui = int(pl.ups.size());
     pl.ups.push_back(u);
   }
@@ -635,6 +645,7 @@ int run_chain(wsu_context* h, const void* img, int img_dtype, int nimg, const vo
     } else if (pl.up_idx[i] >= 0 && (h->use_upres || p.terms != 3)) {
       UpconvParams u = pl.ups[pl.up_idx[i]];
       if (nimg != pl.mb) { u.B = nimg; u.total_boxes = nimg * u.tiles_x * u.tiles_y; }
+      u.tma_store = h->tma_store;
       LAUNCH_TRY(launch_upconv_res(u, 4 * u.co_t, h->num_sms, st));
     } else if (p.ntaps == 9 && (p.terms != 3 || (halo && (h->use_pair == 2 || (h->use_pair == 1 && n_tile == 128))))) {
       p.total_items = ((p.total_sub + 3) / 4) * p.n_tiles;   // pair items: 2 slots x 2 CTAs = 4 boxes
@@ -977,6 +988,7 @@ static int upload_layer(wsu_context* h, const std::string& name, int cin, int co
   CUDA_TRY(cudaMemcpy(lw.wpack, pack.data(), pack.size(), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&lw.bias), size_t(cout) * 4));
   CUDA_TRY(cudaMemcpy(lw.bias, bias_override ? bias_override->data() : b->data.data(), size_t(cout) * 4, cudaMemcpyHostToDevice));
+  lw.bias_host.assign(bias_override ? bias_override->data() : b->data.data(), (bias_override ? bias_override->data() : b->data.data()) + cout);
   h->layers[name] = lw;
   return WSU_OK;
 }

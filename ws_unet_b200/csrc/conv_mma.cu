@@ -169,7 +169,9 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
     }
     return;
   }
-  const bool use_tma = tm != nullptr && !map.border && map.full && g.tw_shift == 3 && !g.up;
+  // (the 8-pixel-wide boxes of the 3x3 kernels with the plain map; the 16-pixel-wide boxes of the up-convolution with the
+  // element-strided map of one output phase)
+  const bool use_tma = tm != nullptr && !map.border && map.full && (g.up ? g.tw_shift == 4 : g.tw_shift == 3);
 #pragma unroll
   for (int plane = 0; plane < 2; ++plane) {
     if (plane >= planes) break;
@@ -186,7 +188,8 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
       __syncwarp();
       if (lane == 0) {
         // padded coordinates: pixel (y, x) lives at (y + 1, x + 1); the warp's 32 rows are box rows (row0 >> 3) .. + 3
-        tma_store_5d(tm, scratch, c0, g.x0 + 1, g.y0 + (row0 >> 3) + 1, g.b, plane);
+        if (g.up) tma_store_5d(tm, scratch, c0, 2 * g.x0 + (g.pos & 1) + 1, 2 * (g.y0 + (row0 >> 4)) + (g.pos >> 1) + 1, g.b, plane);
+        else tma_store_5d(tm, scratch, c0, g.x0 + 1, g.y0 + (row0 >> 3) + 1, g.b, plane);
         tma_store_commit();
       }
       continue;
@@ -1429,7 +1432,13 @@ __global__ void __launch_bounds__(TERMS == 3 ? kUpThreads : kUpThreadsWide, 1) u
         const int col0 = cc * 32;
         const int pos = col0 / p.co_t, cl = col0 % p.co_t;
         uint32_t h[16], l[16];
-        if (p.out.fmt == ACT_F16) {
+        if (p.out.fmt == ACT_F16 && p.zero_bias) {   // reduced plans: the bias lives in the consuming layer (api.cu, commit)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            h[i] = cvt_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            l[i] = 0u;
+          }
+        } else if (p.out.fmt == ACT_F16) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 bq = *reinterpret_cast<const float4*>(sBias + cl + 4 * i);
@@ -1448,13 +1457,14 @@ __global__ void __launch_bounds__(TERMS == 3 ? kUpThreads : kUpThreadsWide, 1) u
         const BoxGeo geo{b, ty * 8, tx * 16, 4, p.H, p.W, 1, pos};
         const StoreMap smap = make_store_map(p.out, geo, lane, quad * 32);   // per chunk: the output phase changes with it
         store_chunk_coalesced(p.out, sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32, nt * p.co_t + cl, h, l, geo,
-                              smap);
+                              smap, p.tma_store ? &p.tmapOut : nullptr);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acs]);
       if (++acs == 2) { acs = 0; acph ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();   // TMA stores out of this warp's staging buffer are complete before the CTA retires
   }
   tc_fence_before();
   __syncthreads();

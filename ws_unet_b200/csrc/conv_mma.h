@@ -90,6 +90,9 @@ struct alignas(64) UpconvParams {
   int B, H, W;            // input dims
   int tiles_x, tiles_y, total_boxes;
   Act out;                // (2H, 2W) destination
+  CUtensorMap tmapOut;    // destination for TMA stores of one output phase: box (32 ch, 16 px, 2 rows), element strides (1, 2, 2)
+  int tma_store;          // 1: interior boxes leave through tmapOut
+  int zero_bias;          // 1: the bias was folded into the consuming layer (reduced plans): nothing to add
 };
 cudaError_t launch_upconv_res(const UpconvParams& p, int n_tile, int num_sms, cudaStream_t stream);
 constexpr int kUpconvResBytes = 131072;  // weight bytes that must fit: cblocks * N_TILE * 256

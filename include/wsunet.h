@@ -69,6 +69,9 @@ int wsu_commit_weights(wsu_handle h);
  *          "tma_store" (default 1: interior boxes of the 3x3 layers leave through TMA tensor stores, bit-identical, 1-3 % of the chain);
  *          "w_resident" (default 1: under precision 3 the layers with one input channel block keep all nine taps' weights in shared memory);
  *          "alias_buffers" (default 1: feature maps with disjoint lifetimes share arena bytes; 0 for layer inspection);
+ *          "dbg" (default 0, also env WSU_DBG: knock-out switches for TIMING EXPERIMENTS - results are wrong when set; bit 0 no
+ *                 pooled output, bit 1 no main-output stores, bit 2 no epilogue work, bit 3 no e4m3 correction MMA, bit 4 staging
+ *                 without global stores, bit 5 per-lane stores without staging; profiles/r02_knockout_timings.md);
  *          "profile" (1: record CUDA events around every layer launch of the last micro-batch) */
 int wsu_set_option(wsu_handle h, const char* key, int64_t value);
 

@@ -85,10 +85,10 @@ __device__ __forceinline__ void store_pixel32(const Act& o, int b, int oy, int o
 
 // store 8 channels (one 16-byte piece per plane) of one pixel to every halo target of (oy, ox)
 __device__ __forceinline__ void store_pixel8(const Act& o, int b, int oy, int ox, int c0, const uint32_t (&h)[4],
-                                             const uint32_t (&l)[4]) {
+                                             const uint32_t (&l)[4], int fmt) {
   const uint4 vh = make_uint4(h[0], h[1], h[2], h[3]), vl = make_uint4(l[0], l[1], l[2], l[3]);
   const size_t off = ((size_t(b) * (o.H + 2) + (oy + 1)) * (o.W + 2) + (ox + 1)) * o.C + c0;
-  const bool two = o.fmt != ACT_F16;   // fp16 maps have one plane (h holds the fp16 words)
+  const bool two = fmt != ACT_F16;   // fp16 maps have one plane (h holds the fp16 words)
   *reinterpret_cast<uint4*>(o.base + off) = vh;
   if (two) *reinterpret_cast<uint4*>(o.base + o.plane + off) = vl;
   if (oy == 1 || ox == 1 || oy == o.H - 2 || ox == o.W - 2) {   // reflect-halo duplicates (border pixels only)
@@ -155,9 +155,10 @@ __device__ __forceinline__ StoreMap make_store_map(const Act& o, const BoxGeo& g
 // L1 / shared-memory path, which the MMA operand reads of these kernels already saturate.
 __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scratch, int lane, int row0, int c0,
                                                       const uint32_t (&h)[16], const uint32_t (&l)[16], const BoxGeo& g,
-                                                      const StoreMap& map, const CUtensorMap* tm = nullptr, int dbg = 0) {
+                                                      const StoreMap& map, const CUtensorMap* tm = nullptr, int dbg = 0,
+                                                      int fmt = -1) {
   const int piece = lane & 3;
-  const int planes = o.fmt == ACT_F16 ? 1 : 2;   // fp16 maps: h holds 32 fp16 channels = the same 64-byte row
+  const int planes = (fmt >= 0 ? fmt : o.fmt) == ACT_F16 ? 1 : 2;   // fp16 maps: h holds 32 fp16 channels = the same 64-byte row
   if ((dbg & 32) && !map.border && map.full) {   // WSU_DBG=32 (experiment): every lane stores its own pixel, no staging
     int oy, ox;
     g.pixel(row0 + lane, oy, ox);
@@ -244,13 +245,17 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&f)[32], float
   }
 }
 
-template <int N_TILE, int EPI, bool STACKED = false>
+// FMT >= 0: the output format (and ACT_F16 for the pooled map) is known at compile time - the kernels of the reduced plans
+// write one format only, and the conversions of the others need not be compiled into them (registers, instruction cache)
+template <int N_TILE, int EPI, bool STACKED = false, int FMT = -1>
 __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* sBias, uint32_t tbase, int b, int y, int x,
                                        bool valid, int nt, int pos, int tx, int ty, int pool_xor, WsAcc& acc,
                                        const BoxGeo& geo, uint8_t* scratch, int lane, int row0) {
   if (p.dbg & 4) return;   // WSU_DBG=4: no epilogue work at all (timing experiment: what the MMA pipeline alone takes)
   if constexpr (EPI == EPI_ACT) {
     const StoreMap smap = make_store_map(p.out, geo, lane, row0);
+    const int fmt = FMT >= 0 ? FMT : p.out.fmt;
+    const int pool_fmt = FMT >= 0 ? int(ACT_F16) : p.pool.fmt;
 #pragma unroll 1
     for (int cc = 0; cc < N_TILE / 32; ++cc) {
       const int n0 = nt * N_TILE + cc * 32;
@@ -266,16 +271,16 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
         for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
       }
       uint32_t h[16], l[16];
-      if (p.out.fmt == ACT_F16) {
+      if (fmt == ACT_F16) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) { h[i] = cvt_f16x2(f[2 * i], f[2 * i + 1]); l[i] = 0u; }
-      } else if (p.out.fmt == ACT_F16F8) {
+      } else if (fmt == ACT_F16F8) {
         pack_f16f8_32(f, h, l);
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
       }
-      if (!(p.dbg & 2)) store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap, p.tma_store ? &p.tmapOut : nullptr, p.dbg);
+      if (!(p.dbg & 2)) store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap, p.tma_store ? &p.tmapOut : nullptr, p.dbg, fmt);
       if (p.do_pool && !(p.dbg & 1)) {
         // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16). Each exchange moves
         // only the half the partner will keep, so the four lanes of a quad end up with 8 channels each of the pooled
@@ -294,14 +299,14 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
         }
         if (valid) {
           uint32_t h4[4], l4[4];
-          if (p.pool.fmt == ACT_F16) {   // max commutes with the (monotone) rounding: pool(fp16(v)) == fp16(pool(v))
+          if (pool_fmt == ACT_F16) {   // max commutes with the (monotone) rounding: pool(fp16(v)) == fp16(pool(v))
 #pragma unroll
             for (int i = 0; i < 4; ++i) { h4[i] = cvt_f16x2(m8[2 * i], m8[2 * i + 1]); l4[i] = 0u; }
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) split_pack2(m8[2 * i], m8[2 * i + 1], h4[i], l4[i]);
           }
-          store_pixel8(p.pool, b, y >> 1, x >> 1, n0 + 16 * int(ox1) + 8 * int(oy1), h4, l4);
+          store_pixel8(p.pool, b, y >> 1, x >> 1, n0 + 16 * int(ox1) + 8 * int(oy1), h4, l4, pool_fmt);
         }
       }
     }
@@ -1239,8 +1244,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
           const uint32_t tbase = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acs * kAccCols + j * C::ACC_W);
           WsAcc acc;
           const BoxGeo geo{bc.b, bc.y0, bc.x0, 3, p.H, p.W, 0, 0};
-          epilogue_box<N_TILE, EPI, C::STACKED>(p, sBias, tbase, bc.b, y, x, valid, nt, 0, tx, ty, kHaloTW, acc, geo,
-                                                sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32);
+          // the one- and two-term kernels write fp16 maps only, the resident-weight kernel fp16 + e4m3 maps (launch_halo2_t checks)
+          constexpr int FMT = TERMS != 3 ? int(ACT_F16) : (RES ? int(ACT_F16F8) : -1);
+          epilogue_box<N_TILE, EPI, C::STACKED, FMT>(p, sBias, tbase, bc.b, y, x, valid, nt, 0, tx, ty, kHaloTW, acc, geo,
+                                                     sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32);
           if constexpr (EPI == EPI_HEAD) {
             if (p.partials) {
               const float wr = warp_sum(acc.wr), w = warp_sum(acc.w), l1 = warp_sum(acc.l1), wb = warp_sum(acc.wb);
@@ -1275,7 +1282,9 @@ template <int N_TILE, int EPI>
 cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream) {
   int pairs = num_sms / 2;
   if (pairs > p.total_items) pairs = p.total_items;
-  const bool res = N_TILE == 64 && p.w_resident && p.f8_blocks && p.cblocks == 1 && !p.src0_f16 && p.n_tiles == 1;
+  const bool fmt_f16 = p.out.fmt == ACT_F16 && (!p.do_pool || p.pool.fmt == ACT_F16);
+  const bool fmt_f16f8 = EPI == EPI_HEAD || (p.out.fmt == ACT_F16F8 && (!p.do_pool || p.pool.fmt == ACT_F16));
+  const bool res = N_TILE == 64 && p.w_resident && p.f8_blocks && p.cblocks == 1 && !p.src0_f16 && p.n_tiles == 1 && fmt_f16f8;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kHaloThreads);
@@ -1295,6 +1304,7 @@ cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream
       return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<64, EPI, true, 3, true>, p);
     }
   }
+  if (p.terms != 3 && !fmt_f16) return cudaErrorInvalidValue;   // the reduced-term kernels are compiled for fp16 outputs
   if constexpr (N_TILE == 128 && EPI == EPI_ACT) {
     if (p.terms == 2) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 2>, p);
     if (p.terms == 1) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 1>, p);

@@ -972,10 +972,16 @@ __device__ __forceinline__ int block_mode(const ConvParams& p, int c) {
 // Tried and dropped (profiles/r02_ab_epilogue_warps_tma_store.log): sixteen epilogue warps per CTA (two per box quarter, half
 // the chunks each, 1 KB of staging per warp) - bit-identical and 13 % slower over the chain: these kernels are bound by the
 // shared-memory data path, which more warps do not widen, and 608 threads leave 96 registers per thread (spills).
-template <int N_TILE, int EPI, bool COLL = true, int TERMS = 3, bool RES = false>
+// W8 (Cout = 64 kernel): 0 = every block mode behind runtime switches (plans 0-2); 1 = the fp16 + fp8 plan with streamed
+// weights (d41: only MODE_F16_1 / MODE_F8 and the fp16 + e4m3 output format are compiled in - the generic kernel is 91 KB of
+// code, which the unrolled single-thread issue loop and the epilogue warps fight over in the instruction cache); 2 = the same
+// with resident weights (e12, d42).
+template <int N_TILE, int EPI, bool COLL = true, int TERMS = 3, int W8 = 0>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __grid_constant__ ConvParams p) {
+  constexpr bool RES = W8 == 2;
+  constexpr bool F8ONLY = W8 != 0;
   static_assert(TERMS == 3 || N_TILE == 128, "the one- and two-term variants exist for the Cout >= 128 layers only");
-  static_assert(!RES || (N_TILE == 64 && TERMS == 3), "resident weights: fp16 + fp8 layers with one channel block");
+  static_assert(!F8ONLY || (N_TILE == 64 && TERMS == 3), "fp16 + fp8 variants: Cout = 64 layers");
   using C = H2Cfg<N_TILE, TERMS, RES>;
   constexpr int M_SUB = C::M_SUB;
 
@@ -1205,6 +1211,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
             };
             if constexpr (RES) {
               issue_block(std::integral_constant<int, MODE_F8>{});
+            } else if constexpr (F8ONLY) {
+              if (block_mode(p, c) == MODE_F8) issue_block(std::integral_constant<int, MODE_F8>{});
+              else issue_block(std::integral_constant<int, MODE_F16_1>{});
             } else if constexpr (C::STACKED) {
               const int mode = block_mode(p, c);
               if (mode == MODE_F8) issue_block(std::integral_constant<int, MODE_F8>{});
@@ -1245,7 +1254,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
           WsAcc acc;
           const BoxGeo geo{bc.b, bc.y0, bc.x0, 3, p.H, p.W, 0, 0};
           // the one- and two-term kernels write fp16 maps only, the resident-weight kernel fp16 + e4m3 maps (launch_halo2_t checks)
-          constexpr int FMT = TERMS != 3 ? int(ACT_F16) : (RES ? int(ACT_F16F8) : -1);
+          constexpr int FMT = TERMS != 3 ? int(ACT_F16) : (F8ONLY ? int(ACT_F16F8) : -1);
           epilogue_box<N_TILE, EPI, C::STACKED, FMT>(p, sBias, tbase, bc.b, y, x, valid, nt, 0, tx, ty, kHaloTW, acc, geo,
                                                      sScratch + (warp - 2) * kScratchPerWarp, lane, quad * 32);
           if constexpr (EPI == EPI_HEAD) {
@@ -1301,7 +1310,11 @@ cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream
     if (res) {
       if (p.terms != 3) return cudaErrorInvalidValue;
       cfg.dynamicSmemBytes = H2Cfg<64, 3, true>::SMEM;
-      return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<64, EPI, true, 3, true>, p);
+      return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<64, EPI, true, 3, 2>, p);
+    }
+    if constexpr (EPI == EPI_ACT) {   // the fp16 + fp8 plan with streamed weights (d41: fp16 source-0 blocks, one MMA per MAC)
+      if (!(p.dbg & 64) && p.f8_blocks && (p.src0_f16 == 0 || p.src0_f16 == 2) && fmt_f16f8 && p.terms == 3)   // WSU_DBG=64: generic kernel (A/B)
+        return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<64, EPI_ACT, true, 3, 1>, p);
     }
   }
   if (p.terms != 3 && !fmt_f16) return cudaErrorInvalidValue;   // the reduced-term kernels are compiled for fp16 outputs
@@ -1517,9 +1530,11 @@ cudaError_t conv_mma_init() {
   e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
   if (e != cudaSuccess) return e;
   static_assert(H2Cfg<64, 3, true>::SMEM <= 232448, "resident-weight variant exceeds the shared memory of an SM");
-  e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_ACT, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64, 3, true>::SMEM);
+  e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_ACT, true, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64, 3, true>::SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_HEAD, true, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64, 3, true>::SMEM);
+  e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_HEAD, true, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64, 3, true>::SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_ACT, true, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upconv_res_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
   if (e != cudaSuccess) return e;

@@ -31,17 +31,6 @@ constexpr int kE11Seg = 128;   // pixels per row segment
 constexpr int kE11Rows = 16;   // rows per CTA (weights are loaded into registers once per CTA)
 constexpr int kE11Pitch = kE11Seg + 4;
 
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
 // kIn: 0 = uint8 pixels (x / 255), 1 = float32 in [0,1], 2 = uint8 pixels, LSB DIFFERENCE image (x_bar - x) / 255 = +-1/255:
 // what the reference feeds the predictor for bias correction, pixel_estimator(x_bar - x) (src/ws/estimate.py:126-127)
 // FMT: ACT_SPLIT or ACT_F16F8 (the two formats a full-resolution map can have)

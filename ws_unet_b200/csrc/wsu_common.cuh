@@ -69,27 +69,6 @@ __device__ __forceinline__ uint32_t cvt_e4m3x2(float lo_elem, float hi_elem) {
   asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi_elem), "f"(lo_elem));
   return r;
 }
-// 32 channels of one pixel (two 16-channel groups) in the ACT_F16F8 layout: h = 16 fp16x2 words (plane 0), l = the 64 bytes
-// [a2s 0..15 | a1q 0..15 | a2s 16..31 | a1q 16..31] of plane 1
-__device__ __forceinline__ void pack_f16f8_32(const float (&f)[32], uint32_t (&h)[16], uint32_t (&l)[16]) {
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {     // word i of a 16-byte run holds channels 16g + 4i .. 16g + 4i + 3
-      const int c = 16 * g + 4 * i;
-      const uint32_t h0 = cvt_f16x2(f[c], f[c + 1]), h1 = cvt_f16x2(f[c + 2], f[c + 3]);
-      h[8 * g + 2 * i] = h0;
-      h[8 * g + 2 * i + 1] = h1;
-      const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
-      const float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
-      l[8 * g + i] = cvt_e4m3x2((f[c] - a01.x) * kF8ScaleA2, (f[c + 1] - a01.y) * kF8ScaleA2) |
-                     (cvt_e4m3x2((f[c + 2] - a23.x) * kF8ScaleA2, (f[c + 3] - a23.y) * kF8ScaleA2) << 16);
-      l[8 * g + 4 + i] = cvt_e4m3x2(f[c] * kF8ScaleA1, f[c + 1] * kF8ScaleA1) |
-                         (cvt_e4m3x2(f[c + 2] * kF8ScaleA1, f[c + 3] * kF8ScaleA1) << 16);
-    }
-  }
-}
-
 // Packed fp32 pair arithmetic (Blackwell FFMA2): acc.{lo,hi} = fma.rn(v, w.{lo,hi}, acc.{lo,hi}) - two independent IEEE
 // fused multiply-adds (bit-identical to two fmaf calls) in one instruction of the FMA pipe.
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
@@ -105,6 +84,46 @@ __device__ __forceinline__ uint64_t fma2_bcast(float v, uint64_t w, uint64_t acc
   asm("mov.b64 %0, {%1, %1};" : "=l"(vv) : "f"(v));   // ptxas folds this into the scalar-broadcast operand form
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(vv), "l"(w), "l"(acc));
   return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// 32 channels of one pixel (two 16-channel groups) in the ACT_F16F8 layout: h = 16 fp16x2 words (plane 0), l = the 64 bytes
+// [a2s 0..15 | a1q 0..15 | a2s 16..31 | a1q 16..31] of plane 1. Packed f32x2 arithmetic: (v - h) 2^14 = fma(h, -2^14, v 2^14)
+// exactly (v - h is representable and the scales are powers of two), so the bytes equal those of the scalar formulation.
+__device__ __forceinline__ void pack_f16f8_32(const float (&f)[32], uint32_t (&h)[16], uint32_t (&l)[16]) {
+  const uint64_t kA2 = pack_f32x2(kF8ScaleA2, kF8ScaleA2), kNegA2 = pack_f32x2(-kF8ScaleA2, -kF8ScaleA2);
+  const uint64_t kA1 = pack_f32x2(kF8ScaleA1, kF8ScaleA1);
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {     // word i of a 16-byte run holds channels 16g + 4i .. 16g + 4i + 3
+      const int c = 16 * g + 4 * i;
+      uint32_t a2[2], a1[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint64_t v = pack_f32x2(f[c + 2 * j], f[c + 2 * j + 1]);
+        const uint32_t hw = cvt_f16x2(f[c + 2 * j], f[c + 2 * j + 1]);
+        h[8 * g + 2 * i + j] = hw;
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw));
+        float r0, r1, s0, s1;
+        unpack_f32x2(fma2(pack_f32x2(hf.x, hf.y), kNegA2, mul2(v, kA2)), r0, r1);
+        unpack_f32x2(mul2(v, kA1), s0, s1);
+        a2[j] = cvt_e4m3x2(r0, r1);
+        a1[j] = cvt_e4m3x2(s0, s1);
+      }
+      l[8 * g + i] = a2[0] | (a2[1] << 16);
+      l[8 * g + 4 + i] = a1[0] | (a1[1] << 16);
+    }
+  }
 }
 
 // Reflect-halo targets of a logical coordinate v in [0,n): storage index v+1, plus the mirrored border

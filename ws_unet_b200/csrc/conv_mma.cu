@@ -236,8 +236,10 @@ __device__ __forceinline__ void load_acc32(uint32_t taddr, float (&f)[32], float
     uint32_t w[32];
     tmem_ld32(taddr + 64, w);
     tmem_ld_wait();
+    const uint64_t cs2 = pack_f32x2(corr_scale, corr_scale);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(w[i]), corr_scale, __uint_as_float(v[i]));
+    for (int i = 0; i < 16; ++i)   // two columns per FFMA2 (the same IEEE fma per lane as the scalar form)
+      unpack_f32x2(fma2(pack_u32x2(w[2 * i], w[2 * i + 1]), cs2, pack_u32x2(v[2 * i], v[2 * i + 1])), f[2 * i], f[2 * i + 1]);
   } else {
     tmem_ld_wait();
 #pragma unroll
@@ -262,18 +264,26 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
       float f[32];
       load_acc32<N_TILE, EPI, STACKED>(tbase + cc * 32, f, (p.dbg & 8) ? 0.f : p.corr_scale);   // WSU_DBG=8: correction MMA off (diagnostic)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {   // 128-bit broadcast loads: 8 instead of 32 shared-memory wavefronts per chunk
+      for (int i = 0; i < 8; ++i) {   // 128-bit broadcast loads: 8 instead of 32 shared-memory wavefronts per chunk; packed adds
         const float4 bq = *reinterpret_cast<const float4*>(sBias + n0 + 4 * i);
-        f[4 * i] += bq.x; f[4 * i + 1] += bq.y; f[4 * i + 2] += bq.z; f[4 * i + 3] += bq.w;
+        unpack_f32x2(add2(pack_f32x2(f[4 * i], f[4 * i + 1]), pack_f32x2(bq.x, bq.y)), f[4 * i], f[4 * i + 1]);
+        unpack_f32x2(add2(pack_f32x2(f[4 * i + 2], f[4 * i + 3]), pack_f32x2(bq.z, bq.w)), f[4 * i + 2], f[4 * i + 3]);
       }
-      if (p.relu) {
+      // fp16 maps: ReLU rides on the conversion (cvt.rn.relu) - also for the pooled map, max-pool and ReLU commute
+      const bool relu_in_cvt = p.relu && fmt == ACT_F16 && (!p.do_pool || pool_fmt == ACT_F16);
+      if (p.relu && !relu_in_cvt) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
       }
       uint32_t h[16], l[16];
       if (fmt == ACT_F16) {
+        if (relu_in_cvt) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { h[i] = cvt_f16x2(f[2 * i], f[2 * i + 1]); l[i] = 0u; }
+          for (int i = 0; i < 16; ++i) { h[i] = cvt_f16x2_relu(f[2 * i], f[2 * i + 1]); l[i] = 0u; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { h[i] = cvt_f16x2(f[2 * i], f[2 * i + 1]); l[i] = 0u; }
+        }
       } else if (fmt == ACT_F16F8) {
         pack_f16f8_32(f, h, l);
       } else {
@@ -300,8 +310,13 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
         if (valid) {
           uint32_t h4[4], l4[4];
           if (pool_fmt == ACT_F16) {   // max commutes with the (monotone) rounding: pool(fp16(v)) == fp16(pool(v))
+            if (relu_in_cvt) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { h4[i] = cvt_f16x2(m8[2 * i], m8[2 * i + 1]); l4[i] = 0u; }
+              for (int i = 0; i < 4; ++i) { h4[i] = cvt_f16x2_relu(m8[2 * i], m8[2 * i + 1]); l4[i] = 0u; }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { h4[i] = cvt_f16x2(m8[2 * i], m8[2 * i + 1]); l4[i] = 0u; }
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) split_pack2(m8[2 * i], m8[2 * i + 1], h4[i], l4[i]);

@@ -63,6 +63,13 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo_elem, float hi_elem) {
   return r;
 }
 
+// the same with ReLU folded into the conversion: max(x, 0) commutes with the (monotone) rounding
+__device__ __forceinline__ uint32_t cvt_f16x2_relu(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+
 // two floats -> two e4m3 bytes (element 0 in the low byte), round to nearest even, saturating to +-448
 __device__ __forceinline__ uint32_t cvt_e4m3x2(float lo_elem, float hi_elem) {
   uint16_t r;
@@ -84,6 +91,16 @@ __device__ __forceinline__ uint64_t fma2_bcast(float v, uint64_t w, uint64_t acc
   asm("mov.b64 %0, {%1, %1};" : "=l"(vv) : "f"(v));   // ptxas folds this into the scalar-broadcast operand form
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(vv), "l"(w), "l"(acc));
   return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack_u32x2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
 }
 __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
   uint64_t d;

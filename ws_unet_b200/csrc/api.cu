@@ -398,6 +398,19 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
   p.total_tiles = p.B * p.tiles_y * p.tiles_x * p.n_tiles * p.npos;
   p.sub_x = (p.W + kHaloTW - 1) / kHaloTW;
   p.sub_y = (p.H + kHaloTH - 1) / kHaloTH;
+  {
+    const uint64_t nmax = uint64_t(p.B) * p.sub_x * p.sub_y * std::max(1, p.n_tiles) + 8;   // largest dividend any kernel forms
+    auto fd = [&](int d) {
+      FastDiv f;
+      f.d = uint32_t(d);
+      f.mode = d == 1 ? 1u : (nmax * uint64_t(d) < (uint64_t(1) << 32) ? 0u : 2u);
+      f.mul = d > 1 ? uint32_t((uint64_t(1) << 32) / uint64_t(d)) + 1u : 0u;
+      return f;
+    };
+    p.fd_sub_x = fd(p.sub_x);
+    p.fd_sub_y = fd(p.sub_y);
+    p.fd_n_tiles = fd(p.n_tiles);
+  }
   p.total_sub = p.B * p.sub_x * p.sub_y;
   p.total_items = ((p.total_sub + halo_msub(lw.n_tile) - 1) / halo_msub(lw.n_tile)) * p.n_tiles;
   p.relu = relu;

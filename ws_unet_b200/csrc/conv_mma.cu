@@ -583,12 +583,17 @@ struct HCfg {
 struct BoxCoord {
   int b, y0, x0, sub_in_img;
 };
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+  if (f.mode == 0) return int(__umulhi(uint32_t(n), f.mul));
+  if (f.mode == 1) return n;
+  return n / int(f.d);
+}
 __device__ __forceinline__ BoxCoord decode_box(const ConvParams& p, int s) {
   BoxCoord c;
-  const int tx = s % p.sub_x;
-  const int r = s / p.sub_x;
-  const int ty = r % p.sub_y;
-  c.b = r / p.sub_y;
+  const int r = fast_div(s, p.fd_sub_x);
+  const int tx = s - r * p.sub_x;
+  c.b = fast_div(r, p.fd_sub_y);
+  const int ty = r - c.b * p.sub_y;
   c.x0 = tx * kHaloTW;
   c.y0 = ty * kHaloTH;
   c.sub_in_img = ty * p.sub_x + tx;
@@ -1050,10 +1055,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
       int as = 0;
       uint32_t aph = 0;
       for (int item = pair; item < items; item += npairs) {
-        const int s0 = (item / p.n_tiles) * (2 * M_SUB);
+        const int s0 = fast_div(item, p.fd_n_tiles) * (2 * M_SUB);
         const int nslot = min(M_SUB, (p.total_sub - s0 + 1) / 2);
         const int item_n = item + npairs;
-        const int s0_n = (item_n / p.n_tiles) * (2 * M_SUB);
+        const int s0_n = fast_div(item_n, p.fd_n_tiles) * (2 * M_SUB);
         const int nslot_n = (p.l2_prefetch && item_n < items) ? min(M_SUB, (p.total_sub - s0_n + 1) / 2) : 0;
         for (int c = 0; c < p.cblocks; ++c) {
           const bool src0 = c < p.cblocks0;
@@ -1095,7 +1100,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
         }
       } else
       for (int item = pair; item < items; item += npairs) {
-        const int nt = item % p.n_tiles;
+        const int nt = item - fast_div(item, p.fd_n_tiles) * p.n_tiles;
         for (int q = 0; q < chunks; ++q) {
           uint8_t* dst = sW + ws * C::W_SLOT;
           mbar_wait(&w_empty[ws], wph ^ 1);
@@ -1137,7 +1142,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
         int as = 0, ws = 0, acs = 0;
         uint32_t aph = 0, wph = 0, acph = 0;
         for (int item = pair; item < items; item += npairs) {
-          const int s0 = (item / p.n_tiles) * (2 * M_SUB);
+          const int s0 = fast_div(item, p.fd_n_tiles) * (2 * M_SUB);
           const int nslot = min(M_SUB, (p.total_sub - s0 + 1) / 2);
           mbar_wait(&acc_empty[acs], acph ^ 1);
           tc_fence_after();
@@ -1253,8 +1258,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
     int acs = 0;
     uint32_t acph = 0;
     for (int item = pair; item < items; item += npairs) {
-      const int nt = item % p.n_tiles;
-      const int s0 = (item / p.n_tiles) * (2 * M_SUB);
+      const int nt = item - fast_div(item, p.fd_n_tiles) * p.n_tiles;
+      const int s0 = fast_div(item, p.fd_n_tiles) * (2 * M_SUB);
       const int nslot = min(M_SUB, (p.total_sub - s0 + 1) / 2);
       mbar_wait(&acc_full[acs], acph);
       tc_fence_after();

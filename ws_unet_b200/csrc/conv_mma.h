@@ -10,6 +10,13 @@ namespace wsu {
 enum : int { EPI_ACT = 0, EPI_HEAD = 1 };
 
 // One launch = one layer of UNet.forward (src/unet/model/unet.py:141-189) over a micro-batch.
+// n / d for 0 <= n with n * d < 2^32 by one multiply-high (the per-box index arithmetic of the persistent kernels ran two to
+// three full integer divisions per box and warp: ~100 of the ~800 instructions an epilogue warp spends on a box)
+struct FastDiv {
+  uint32_t mul;    // floor(2^32 / d) + 1
+  uint32_t mode;   // 0: multiply-high, 1: d == 1, 2: generic division (ranges too large for the shortcut)
+  uint32_t d;
+};
 struct alignas(64) ConvParams {
   CUtensorMap tmapA0;  // first concat source  (upsampled path, unet.py:178 puts it first)
   CUtensorMap tmapA1;  // second concat source (skip); unused when cblocks == cblocks0
@@ -19,6 +26,7 @@ struct alignas(64) ConvParams {
   CUtensorMap tmapW32; // same, box = 32 rows (stacked Cout = 64 pair kernel: half of the 64-row Whi tile)
   CUtensorMap tmapOut; // destination map, box (32 ch, 8 px, 4 rows, 1 img, 1 plane), SWIZZLE_64B: TMA stores of the halo kernels
   int tma_store;       // 1: interior boxes leave through tmapOut
+  FastDiv fd_sub_x, fd_sub_y, fd_n_tiles;   // divisions by sub_x, sub_y, n_tiles
   int w_resident;      // fp16 + fp8 layers with one input channel block keep all nine taps' weights in shared memory
   const uint8_t* wpack;  // packed + pre-swizzled split-bf16 weights, see pack_conv_weights()
   const float* bias;     // [Cout]

@@ -122,8 +122,7 @@ struct BoxGeo {
 // 32-channel chunk and both planes. Lane l re-reads pixel q = (l >> 2) + 8 i, piece l & 3 from the staging buffer.
 // `border`: at least one of the warp's pixels also owns reflect-halo slots -> the generic path writes the duplicates.
 struct StoreMap {
-  size_t off[4];   // element offset of (pixel, channel 0) in a plane; only meaningful where (valid >> i) & 1
-  uint32_t valid;
+  uint32_t valid;  // bit i: pixel q = (lane >> 2) + 8 i of the warp's 32 lies inside the map
   bool border;
   bool full;       // every pixel of the warp's 32 lies inside the map (no ragged edge)
 };
@@ -136,13 +135,49 @@ __device__ __forceinline__ StoreMap make_store_map(const Act& o, const BoxGeo& g
     const int q = (lane >> 2) + 8 * i;
     int oy, ox;
     const bool ok = g.pixel(row0 + q, oy, ox);
-    m.off[i] = ((size_t(g.b) * (o.H + 2) + (oy + 1)) * (o.W + 2) + (ox + 1)) * o.C;
     m.valid |= uint32_t(ok) << i;
     edge |= ok && (oy == 1 || ox == 1 || oy == o.H - 2 || ox == o.W - 2);
   }
   m.border = __any_sync(0xffffffffu, edge);
   m.full = __all_sync(0xffffffffu, m.valid == 0xfu);
   return m;
+}
+// element offset of (pixel q of the warp, channel 0) in a plane - only the per-lane store path needs it (interior boxes leave
+// through TMA stores), so it is formed there instead of once per box for every warp
+__device__ __forceinline__ size_t store_offset(const Act& o, const BoxGeo& g, int row) {
+  int oy, ox;
+  g.pixel(row, oy, ox);
+  return ((size_t(g.b) * (o.H + 2) + (oy + 1)) * (o.W + 2) + (ox + 1)) * o.C;
+}
+
+// MaxPool2d(2, 2) of a chunk whose fp16 plane sits in the staging buffer (rows = the warp's 4 x 8 pixels, 64 bytes each, pieces
+// XOR-swizzled as written by store_chunk_coalesced): lane (pp = lane / 4, piece = lane % 4) reads the piece of the four source
+// pixels of pooled pixel pp and takes the maximum on packed halves - max commutes with the fp16 rounding and with ReLU, so this
+// equals converting the pooled fp32 values. 4 LDS + 12 HMNMX2 + 1 store per lane instead of 24 shuffles, 24 FMNMX and 48 selects.
+__device__ __forceinline__ void pool_from_staging(const Act& pool, const uint8_t* scratch, int lane, int row0, int c0,
+                                                  const BoxGeo& g) {
+  const int pp = lane >> 2, piece = lane & 3;
+  const int py = pp >> 2, px = pp & 3;
+  uint4 m;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int r = (2 * py + (k >> 1)) * 8 + 2 * px + (k & 1);
+    const uint4 v = *reinterpret_cast<const uint4*>(scratch + r * kScratchPitch + ((piece ^ ((r >> 1) & 3)) << 4));
+    if (k == 0) {
+      m = v;
+    } else {
+      auto hmax = [](uint32_t a, uint32_t b) {
+        const __half2 r2 = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+        return *reinterpret_cast<const uint32_t*>(&r2);
+      };
+      m = make_uint4(hmax(m.x, v.x), hmax(m.y, v.y), hmax(m.z, v.z), hmax(m.w, v.w));
+    }
+  }
+  const int y = g.y0 + (row0 >> 3) + 2 * py, x = g.x0 + 2 * px;   // top-left source pixel (H, W are even where a pool exists)
+  if (y < g.H && x < g.W) {
+    const uint32_t h4[4] = {m.x, m.y, m.z, m.w}, l4[4] = {0u, 0u, 0u, 0u};
+    store_pixel8(pool, g.b, y >> 1, x >> 1, c0 + piece * 8, h4, l4, ACT_F16);
+  }
 }
 
 // Warp-cooperative store of one 32-channel chunk of the warp's 32 pixels. Registers hold "my pixel, 32 channels";
@@ -156,7 +191,7 @@ __device__ __forceinline__ StoreMap make_store_map(const Act& o, const BoxGeo& g
 __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scratch, int lane, int row0, int c0,
                                                       const uint32_t (&h)[16], const uint32_t (&l)[16], const BoxGeo& g,
                                                       const StoreMap& map, const CUtensorMap* tm = nullptr, int dbg = 0,
-                                                      int fmt = -1) {
+                                                      int fmt = -1, const Act* pool = nullptr) {
   const int piece = lane & 3;
   const int planes = (fmt >= 0 ? fmt : o.fmt) == ACT_F16 ? 1 : 2;   // fp16 maps: h holds 32 fp16 channels = the same 64-byte row
   if ((dbg & 32) && !map.border && map.full) {   // WSU_DBG=32 (experiment): every lane stores its own pixel, no staging
@@ -193,9 +228,11 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
         else tma_store_5d(tm, scratch, c0, g.x0 + 1, g.y0 + (row0 >> 3) + 1, g.b, plane);
         tma_store_commit();
       }
+      if (plane == 0 && pool != nullptr) pool_from_staging(*pool, scratch, lane, row0, c0, g);
       continue;
     }
     __syncwarp();
+    if (plane == 0 && pool != nullptr) pool_from_staging(*pool, scratch, lane, row0, c0, g);
     __nv_bfloat16* base = o.base + (plane ? o.plane : 0) + c0 + piece * 8;
     if (!map.border) {
       // interior box: one store per (pixel, piece), addresses from the per-box map
@@ -203,7 +240,7 @@ __device__ __forceinline__ void store_chunk_coalesced(const Act& o, uint8_t* scr
       for (int i = 0; i < 4; ++i) {
         const int q = (lane >> 2) + 8 * i;
         const uint4 v = *reinterpret_cast<const uint4*>(scratch + q * kScratchPitch + ((piece ^ ((q >> 1) & 3)) << 4));
-        if (((map.valid >> i) & 1) && !(dbg & 16)) *reinterpret_cast<uint4*>(base + map.off[i]) = v;   // WSU_DBG=16: staging without the global stores
+        if (((map.valid >> i) & 1) && !(dbg & 16)) *reinterpret_cast<uint4*>(base + store_offset(o, g, row0 + q)) = v;   // WSU_DBG=16: staging without the global stores
       }
     } else {
 #pragma unroll
@@ -290,8 +327,12 @@ __device__ __forceinline__ void epilogue_box(const ConvParams& p, const float* s
 #pragma unroll
         for (int i = 0; i < 16; ++i) split_pack2(f[2 * i], f[2 * i + 1], h[i], l[i]);
       }
-      if (!(p.dbg & 2)) store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap, p.tma_store ? &p.tmapOut : nullptr, p.dbg, fmt);
-      if (p.do_pool && !(p.dbg & 1)) {
+      // fp16 / fp16 + e4m3 maps with an fp16 pooled map: the pool is taken from the staged fp16 plane inside the store
+      const bool staged_pool = p.do_pool && !(p.dbg & 3) && pool_fmt == ACT_F16 && (fmt == ACT_F16 || fmt == ACT_F16F8) && p.relu &&
+                               geo.tw_shift == 3 && !geo.up;
+      if (!(p.dbg & 2)) store_chunk_coalesced(p.out, scratch, lane, row0, n0, h, l, geo, smap, p.tma_store ? &p.tmapOut : nullptr, p.dbg, fmt,
+                                              staged_pool ? &p.pool : nullptr);
+      if (p.do_pool && !(p.dbg & 1) && !staged_pool) {
         // 2x2 max over (x^1, y^1): with TW == 16 both partners live in this warp (lane^1, lane^16). Each exchange moves
         // only the half the partner will keep, so the four lanes of a quad end up with 8 channels each of the pooled
         // pixel (24 shuffles per chunk instead of 64) and every lane stores one 16-byte piece per plane.

@@ -444,6 +444,19 @@ int add_conv(wsu_context* h, Plan& pl, const std::string& lname, const LayerW& l
     u.tiles_x = (u.W + 15) / 16;
     u.tiles_y = (u.H + 7) / 8;
     u.total_boxes = u.B * u.tiles_x * u.tiles_y;
+    {
+      const uint64_t nmax = uint64_t(u.total_boxes) + 1024;
+      auto fd = [&](int d) {
+        FastDiv f;
+        f.d = uint32_t(d);
+        f.mode = d == 1 ? 1u : (nmax * uint64_t(d) < (uint64_t(1) << 32) ? 0u : 2u);
+        f.mul = d > 1 ? uint32_t((uint64_t(1) << 32) / uint64_t(d)) + 1u : 0u;
+        return f;
+      };
+      u.fd_tiles_x = fd(u.tiles_x);
+      u.fd_tiles_y = fd(u.tiles_y);
+      u.fd_co_t = fd(u.co_t);
+    }
     u.out = *out;
     if ((rc = make_out_tmap(&u.tmapOut, *out, true))) return rc;
     u.zero_bias = std::all_of(lw.bias_host.begin(), lw.bias_host.end(), [](float v) { return v == 0.f; }) ? 1 : 0;

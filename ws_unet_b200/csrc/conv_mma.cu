@@ -1453,8 +1453,8 @@ __global__ void __launch_bounds__(TERMS == 3 ? kUpThreads : kUpThreadsWide, 1) u
       int as = 0;
       uint32_t aph = 0;
       for (int box = first_box; box < p.total_boxes; box += box_step) {
-        const int tx = box % p.tiles_x, r = box / p.tiles_x;
-        const int ty = r % p.tiles_y, b = r / p.tiles_y;
+        const int r = fast_div(box, p.fd_tiles_x), tx = box - r * p.tiles_x;
+        const int b = fast_div(r, p.fd_tiles_y), ty = r - b * p.tiles_y;
         for (int c = 0; c < p.cblocks; ++c) {
           mbar_wait(&a_empty[as], aph ^ 1);
           mbar_arrive_expect_tx(&a_full[as], kBoxBytes);
@@ -1501,8 +1501,8 @@ __global__ void __launch_bounds__(TERMS == 3 ? kUpThreads : kUpThreadsWide, 1) u
     uint32_t acph = 0;
     constexpr int kChunks = N_TILE / 32;
     for (int box = first_box; box < p.total_boxes; box += box_step) {
-      const int tx = box % p.tiles_x, r = box / p.tiles_x;
-      const int ty = r % p.tiles_y, b = r / p.tiles_y;
+      const int r = fast_div(box, p.fd_tiles_x), tx = box - r * p.tiles_x;
+      const int b = fast_div(r, p.fd_tiles_y), ty = r - b * p.tiles_y;
       const int y = ty * 8 + ty_in, x = tx * 16 + tx_in;
       const bool valid = (y < p.H) && (x < p.W);
       mbar_wait(&acc_full[acs], acph);
@@ -1514,7 +1514,7 @@ __global__ void __launch_bounds__(TERMS == 3 ? kUpThreads : kUpThreadsWide, 1) u
         tmem_ld32(tbase + cc * 32, v);
         tmem_ld_wait();
         const int col0 = cc * 32;
-        const int pos = col0 / p.co_t, cl = col0 % p.co_t;
+        const int pos = fast_div(col0, p.fd_co_t), cl = col0 - pos * p.co_t;
         uint32_t h[16], l[16];
         if (p.out.fmt == ACT_F16 && p.zero_bias) {   // reduced plans: the bias lives in the consuming layer (api.cu, commit)
 #pragma unroll

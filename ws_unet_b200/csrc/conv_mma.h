@@ -101,6 +101,7 @@ struct alignas(64) UpconvParams {
   CUtensorMap tmapOut;    // destination for TMA stores of one output phase: box (32 ch, 16 px, 2 rows), element strides (1, 2, 2)
   int tma_store;          // 1: interior boxes leave through tmapOut
   int zero_bias;          // 1: the bias was folded into the consuming layer (reduced plans): nothing to add
+  FastDiv fd_tiles_x, fd_tiles_y, fd_co_t;   // divisions by tiles_x, tiles_y, co_t
 };
 cudaError_t launch_upconv_res(const UpconvParams& p, int n_tile, int num_sms, cudaStream_t stream);
 constexpr int kUpconvResBytes = 131072;  // weight bytes that must fit: cblocks * N_TILE * 256

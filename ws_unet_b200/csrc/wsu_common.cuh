@@ -113,12 +113,28 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
   return d;
 }
 
+// fp32 = fp16 * fp16 + fp32 in one instruction (FHFMA): element 0 / 1 of the packed halves h2 times element 0 of k2, plus c
+__device__ __forceinline__ float fhfma_lo(uint32_t h2, uint32_t k2, float c) {
+  float d;
+  asm("{ .reg .b16 hl, hh, kl, kh; mov.b32 {hl, hh}, %1; mov.b32 {kl, kh}, %2; fma.rn.f32.f16 %0, hl, kl, %3; }"
+      : "=f"(d) : "r"(h2), "r"(k2), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float fhfma_hi(uint32_t h2, uint32_t k2, float c) {
+  float d;
+  asm("{ .reg .b16 hl, hh, kl, kh; mov.b32 {hl, hh}, %1; mov.b32 {kl, kh}, %2; fma.rn.f32.f16 %0, hh, kl, %3; }"
+      : "=f"(d) : "r"(h2), "r"(k2), "f"(c));
+  return d;
+}
+
 // 32 channels of one pixel (two 16-channel groups) in the ACT_F16F8 layout: h = 16 fp16x2 words (plane 0), l = the 64 bytes
 // [a2s 0..15 | a1q 0..15 | a2s 16..31 | a1q 16..31] of plane 1. Packed f32x2 arithmetic: (v - h) 2^14 = fma(h, -2^14, v 2^14)
 // exactly (v - h is representable and the scales are powers of two), so the bytes equal those of the scalar formulation.
 __device__ __forceinline__ void pack_f16f8_32(const float (&f)[32], uint32_t (&h)[16], uint32_t (&l)[16]) {
-  const uint64_t kA2 = pack_f32x2(kF8ScaleA2, kF8ScaleA2), kNegA2 = pack_f32x2(-kF8ScaleA2, -kF8ScaleA2);
+  static_assert(kF8ScaleA2 == 16384.f, "kNegA2h below is -2^14 as an fp16 bit pattern");
+  const uint64_t kA2 = pack_f32x2(kF8ScaleA2, kF8ScaleA2);
   const uint64_t kA1 = pack_f32x2(kF8ScaleA1, kF8ScaleA1);
+  const uint32_t kNegA2h = 0xF400F400u;   // (-16384, -16384) as packed halves
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
 #pragma unroll
@@ -130,9 +146,9 @@ __device__ __forceinline__ void pack_f16f8_32(const float (&f)[32], uint32_t (&h
         const uint64_t v = pack_f32x2(f[c + 2 * j], f[c + 2 * j + 1]);
         const uint32_t hw = cvt_f16x2(f[c + 2 * j], f[c + 2 * j + 1]);
         h[8 * g + 2 * i + j] = hw;
-        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw));
-        float r0, r1, s0, s1;
-        unpack_f32x2(fma2(pack_f32x2(hf.x, hf.y), kNegA2, mul2(v, kA2)), r0, r1);
+        float e0, e1, s0, s1;
+        unpack_f32x2(mul2(v, kA2), e0, e1);
+        const float r0 = fhfma_lo(hw, kNegA2h, e0), r1 = fhfma_hi(hw, kNegA2h, e1);   // (v - h) 2^14, the halves read in place
         unpack_f32x2(mul2(v, kA1), s0, s1);
         a2[j] = cvt_e4m3x2(r0, r1);
         a1[j] = cvt_e4m3x2(s0, s1);

@@ -16,6 +16,11 @@ for nsteps, (h, w) in ((2, (40, 72)), (2, (64, 96)), (1, (34, 50)), (0, (24, 40)
     b, l1, y = W.ws_estimate(img, m, weighted=1, clip=True, return_l1=True, return_prediction=True)
     b0 = W.ws_estimate(img, m, weighted=0, clip=False)
     print('unet', nsteps, h, w, b.tolist(), b0.tolist())
+    if nsteps in (1, 2):      # the reduced precision plans: fp16 maps, fp16 + e4m3 maps, resident weights, TMA stores, staged pooling
+        for mode in ('fp16x1', 'fp16x1_f8'):
+            m.set_precision(mode)
+            bq = W.ws_estimate(img, m, weighted=1, clip=True, correct_bias=True)
+            print('  ', mode, m.active_precision(dev), bq.tolist())
 for h, w in ((3, 16), (5, 32), (66, 528), (35, 516), (130, 1040)):
     img = torch.from_numpy(rng.integers(0, 256, (9, 1, h, w), dtype=np.uint8)).to(dev)
     for name in ('KB', 'AVG'):

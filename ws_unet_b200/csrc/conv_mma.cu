@@ -1009,7 +1009,7 @@ struct H2Cfg {
   static constexpr int M_SUB = 2;                 // box slots per item (x 2 CTAs = 4 boxes share one weight pass)
   static constexpr int ACC_W = 128;
   static constexpr int A_BYTES = TERMS == 3 ? kHaloABytes : kHaloABytes / 2;
-  static constexpr int SA = TERMS == 3 ? 3 : (TERMS == 2 ? 4 : 6);   // fp16 boxes are 22.5 KB: an even count keeps the weight ring 1024-byte aligned
+  static constexpr int SA = TERMS == 3 ? 3 : ((TERMS == 2 || RES) ? 4 : 6);   // one-term + resident weights: four boxes leave room for the nine 8 KB taps   // fp16 boxes are 22.5 KB: an even count keeps the weight ring 1024-byte aligned
   static constexpr int W_SLOT = (TERMS == 1 || RES) ? 8192 : 16384;   // [X tile 8 KB][Y tile 4 KB (stacked) | Z tile 8 KB]; RES: [fp16 4 KB][e4m3 4 KB]
   static constexpr int W_BYTES = STACKED ? 12288 : (TERMS == 1 ? 8192 : 16384);
   // a tap's weights are consumed in 2 x 4 MMAs: ~1500 / 1000 / 540 cycles with 3 / 2 / 1 terms, against an L2 -> shared
@@ -1039,10 +1039,11 @@ __device__ __forceinline__ int block_mode(const ConvParams& p, int c) {
 // with resident weights (e12, d42).
 template <int N_TILE, int EPI, bool COLL = true, int TERMS = 3, int W8 = 0>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __grid_constant__ ConvParams p) {
-  constexpr bool RES = W8 == 2;
-  constexpr bool F8ONLY = W8 != 0;
+  constexpr bool RES = W8 == 2;                       // all nine taps of the (single) channel block stay in shared memory
+  constexpr bool F8ONLY = W8 != 0 && N_TILE == 64;
   static_assert(TERMS == 3 || N_TILE == 128, "the one- and two-term variants exist for the Cout >= 128 layers only");
-  static_assert(!F8ONLY || (N_TILE == 64 && TERMS == 3), "fp16 + fp8 variants: Cout = 64 layers");
+  static_assert(W8 == 0 || (N_TILE == 64 && TERMS == 3) || (N_TILE == 128 && TERMS == 1 && W8 == 2),
+                "W8: fp16 + fp8 variants of the Cout = 64 kernel, or the one-term Cout = 128 kernel with resident weights (e21)");
   using C = H2Cfg<N_TILE, TERMS, RES>;
   constexpr int M_SUB = C::M_SUB;
 
@@ -1135,8 +1136,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
             const uint32_t full_leader = mapa_u32(smem_u32(&w_full[q]), 0);
             const int row0 = q * 2 * N_TILE;
             if (leader) mbar_arrive_expect_tx(&w_full[q], 2 * 8192);
-            tma_load_2d_2sm(dst, &p.tmapW32, full_leader, 0, row0 + int(rank) * 32);
-            tma_load_2d_2sm(dst + 4096, &p.tmapW32, full_leader, 0, row0 + 64 + int(rank) * 32);
+            if constexpr (N_TILE == 64) {
+              tma_load_2d_2sm(dst, &p.tmapW32, full_leader, 0, row0 + int(rank) * 32);
+              tma_load_2d_2sm(dst + 4096, &p.tmapW32, full_leader, 0, row0 + 64 + int(rank) * 32);
+            } else {
+              tma_load_2d_2sm(dst, &p.tmapW, full_leader, 0, row0 + int(rank) * 64);   // this CTA's 64 rows of the fp16 tile
+            }
           }
         }
       } else
@@ -1270,7 +1275,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo2_kernel(const __gri
                 }
               }
             };
-            if constexpr (RES) {
+            if constexpr (RES && N_TILE == 64) {
               issue_block(std::integral_constant<int, MODE_F8>{});
             } else if constexpr (F8ONLY) {
               if (block_mode(p, c) == MODE_F8) issue_block(std::integral_constant<int, MODE_F8>{});
@@ -1379,6 +1384,12 @@ cudaError_t launch_halo2_t(const ConvParams& p, int num_sms, cudaStream_t stream
     }
   }
   if (p.terms != 3 && !fmt_f16) return cudaErrorInvalidValue;   // the reduced-term kernels are compiled for fp16 outputs
+  if constexpr (N_TILE == 128 && EPI == EPI_ACT) {
+    if (p.terms == 1 && p.w_resident && p.cblocks == 1 && p.n_tiles == 1) {   // e21: 72 KB of weights per CTA, loaded once
+      cfg.dynamicSmemBytes = H2Cfg<128, 1, true>::SMEM;
+      return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 1, 2>, p);
+    }
+  }
   if constexpr (N_TILE == 128 && EPI == EPI_ACT) {
     if (p.terms == 2) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 2>, p);
     if (p.terms == 1) return cudaLaunchKernelEx(&cfg, conv_halo2_kernel<128, EPI_ACT, true, 1>, p);
@@ -1596,6 +1607,9 @@ cudaError_t conv_mma_init() {
   e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_HEAD, true, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64, 3, true>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo2_kernel<64, EPI_ACT, true, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<64>::SMEM);
+  if (e != cudaSuccess) return e;
+  static_assert(H2Cfg<128, 1, true>::SMEM <= 232448, "resident-weight variant exceeds the shared memory of an SM");
+  e = cudaFuncSetAttribute(conv_halo2_kernel<128, EPI_ACT, true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, H2Cfg<128, 1, true>::SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(upconv_res_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpSmem);
   if (e != cudaSuccess) return e;

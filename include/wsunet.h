@@ -67,7 +67,8 @@ int wsu_commit_weights(wsu_handle h);
  *          "upconv_resident" (default 1: transposed convs keep their weights in shared memory; 0: per-phase kernel);
  *          "halo" (default 1: 3x3 layers load one haloed box per channel block; 0: per-tap reload kernel);
  *          "tma_store" (default 1: interior boxes of the 3x3 layers leave through TMA tensor stores, bit-identical, 1-3 % of the chain);
- *          "w_resident" (default 1: under precision 3 the layers with one input channel block keep all nine taps' weights in shared memory);
+ *          "w_resident" (default 1: under the reduced plans the 3x3 layers with ONE input channel block - e12, d42 under precision 3,
+ *                        e21 under precision 2 / 3 - keep all nine taps' weights in shared memory instead of streaming them per item);
  *          "alias_buffers" (default 1: feature maps with disjoint lifetimes share arena bytes; 0 for layer inspection);
  *          "dbg" (default 0, also env WSU_DBG: knock-out switches for TIMING EXPERIMENTS - results are wrong when set; bit 0 no
  *                 pooled output, bit 1 no main-output stores, bit 2 no epilogue work, bit 3 no e4m3 correction MMA, bit 4 staging

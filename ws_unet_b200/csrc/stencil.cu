@@ -150,8 +150,10 @@ __global__ void __launch_bounds__(256, 2) first_conv_kernel(const void* __restri
       if constexpr (FMT == ACT_F16F8) {
         // plane 0: 8 fp16 values; plane 1: l[0..1] = the 8 a2s bytes e4m3((v - fp16 v) 2^14), l[2..3] = the 8 a1q bytes e4m3(8 v).
         // (v - h) 2^14 = fma(h, -2^14, v 2^14) exactly: v - h is representable and the scale is a power of two.
-        const uint64_t kA2 = pack_f32x2(kF8ScaleA2, kF8ScaleA2), kNegA2 = pack_f32x2(-kF8ScaleA2, -kF8ScaleA2);
+        static_assert(kF8ScaleA2 == 16384.f, "kNegA2h below is -2^14 as an fp16 bit pattern");
+        const uint64_t kA2 = pack_f32x2(kF8ScaleA2, kF8ScaleA2);
         const uint64_t kA1 = pack_f32x2(kF8ScaleA1, kF8ScaleA1);
+        const uint32_t kNegA2h = 0xF400F400u;
         uint32_t a2[4], a1[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -160,9 +162,9 @@ __global__ void __launch_bounds__(256, 2) first_conv_kernel(const void* __restri
           const uint64_t v = pack_f32x2(fmaxf(v0, 0.f), fmaxf(v1f, 0.f));
           unpack_f32x2(v, v0, v1f);
           h[i] = cvt_f16x2(v0, v1f);
-          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
-          float r0, r1, s0, s1;
-          unpack_f32x2(fma2(pack_f32x2(hf.x, hf.y), kNegA2, mul2(v, kA2)), r0, r1);
+          float e0, e1, s0, s1;
+          unpack_f32x2(mul2(v, kA2), e0, e1);
+          const float r0 = fhfma_lo(h[i], kNegA2h, e0), r1 = fhfma_hi(h[i], kNegA2h, e1);   // one FHFMA per value, halves read in place
           unpack_f32x2(mul2(v, kA1), s0, s1);
           a2[i] = cvt_e4m3x2(r0, r1);
           a1[i] = cvt_e4m3x2(s0, s1);
